@@ -1,0 +1,143 @@
+/*
+ * prt_b200.h -- C ABI of the B200-native (sm_100a) nearest-hit backend for portableRT.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Every entry point
+ * names the reference interface it stands behind (file:line in the portableRT checkout).  The C++
+ * plugin class `portableRT::CUDABackend` (include/portableRT/intersect_cuda.hpp in this repo) and
+ * the Python host mirror (portablert_b200/) are thin callers of exactly these functions.
+ *
+ * Conventions: every int-returning call returns PRT_OK (0) or a PRT_E_* code and never throws;
+ * prt_b200_last_error() gives the message.  A context is used from one host thread at a time, like
+ * the reference's unsynchronised globals (backend.hpp:39,73).  There is NO CPU fallback: without a
+ * compute-capability-10.x device prt_b200_create fails with PRT_E_NO_DEVICE.
+ */
+#ifndef PRT_B200_H
+#define PRT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRT_B200_ABI_VERSION 1
+
+enum {
+	PRT_OK = 0,
+	PRT_E_NO_DEVICE = 1, /* no CC 10.x GPU visible */
+	PRT_E_CUDA = 2,      /* a CUDA runtime call or kernel failed */
+	PRT_E_ARG = 3,       /* bad argument (NULL, bad tag mask, bad layout) */
+	PRT_E_OOM = 4,       /* device or pinned-host allocation failed */
+	PRT_E_LIMIT = 5      /* more than 2^31-2 triangles */
+};
+
+/* Tag mask bits, in the reference's canonical tag order uv,t,primitive_id,p,valid
+ * (hitreg.hpp:24-26, filter tags hitreg.hpp:48-54).  One of 31 kernel specialisations is picked
+ * per non-empty mask -- the analogue of the 31 OptiX raygen programs (hitreg.hpp:142-177). */
+enum { PRT_TAG_UV = 1, PRT_TAG_T = 2, PRT_TAG_PID = 4, PRT_TAG_P = 8, PRT_TAG_VALID = 16, PRT_TAG_ALL = 31 };
+
+/* Byte layout of one HitReg<Tags...> record (hitreg.hpp:29-44); -1 = field absent.  The C++ shim
+ * fills it with sizeof/offsetof of the reference's own type, so nothing is hard-coded here. */
+typedef struct {
+	uint32_t stride;
+	int32_t off_u, off_v, off_t, off_pid, off_valid, off_px, off_py, off_pz;
+} prt_hit_layout;
+
+/* SoA outputs of the device-resident entry point; a NULL pointer for a tag absent from the mask.
+ * uv: float2[n]; t: float[n]; pid: uint32[n]; p: float[3n] packed xyz; valid: uint8[n]. */
+typedef struct {
+	float *uv;
+	float *t;
+	uint32_t *pid;
+	float *p;
+	uint8_t *valid;
+} prt_soa_out;
+
+/* Traversal knobs (there is no other configuration channel in the reference API; the C++ backend
+ * reads the same knobs from PRT_B200_* environment variables in init()). */
+typedef struct {
+	int prune;        /* 1 (default): cull subtrees whose entry distance exceeds the best hit so far
+	                     (+ slack); 0: visit every box the line touches, like bvh.hpp:224-265 */
+	float slack_rel;  /* pruning slack, relative to |t_best| (default 1e-4) */
+	float slack_ulps; /* extra absolute slack in units of ulp(|origin|/|direction|) (default 64) */
+} prt_trace_opts;
+
+typedef struct prt_b200 prt_b200; /* opaque: owns streams, scratch, the BVH, staging buffers */
+
+/* Backend::is_available (backend.hpp:20), evaluated during static initialisation
+ * (backend.hpp:85-95): number of visible devices with compute capability 10.x; 0 when there is no
+ * driver/GPU.  Never fails, never throws, cheap. */
+int prt_b200_device_count(void);
+
+/* Backend::init (backend.hpp:21), called by select_backend (src/backend.cpp:50-56), possibly more
+ * than once.  device < 0 selects env PRT_B200_DEVICE or the first CC 10.x device. */
+int prt_b200_create(prt_b200 **out, int device);
+
+/* Backend::shutdown (backend.hpp:22); NULL-safe, frees all device and pinned memory. */
+void prt_b200_destroy(prt_b200 *ctx);
+
+/* Backend::device_name (backend.hpp:23); returns the length written (excluding NUL). */
+int prt_b200_device_name(const prt_b200 *ctx, char *buf, size_t cap);
+
+/* Backend::set_tris(const Tris&) (backend.hpp:19; CPU: src/intersect_cpu.cpp:12 -> BVH2::build,
+ * bvh.hpp:158-193).  tris9: HOST pointer, n_tris records of 9 floats (v0,v1,v2 xyz, 36-byte
+ * stride, core.hpp:24).  Copies to the device and builds the LBVH there.  n_tris == 0 is legal
+ * (every ray then misses, bvh.hpp:136-137). */
+int prt_b200_set_tris(prt_b200 *ctx, const float *tris9, uint64_t n_tris);
+
+/* Same, triangles already resident on the context's device (device pointer, same 36-byte
+ * records; the buffer is only read).  *build_ms (may be NULL) = device time of the whole build
+ * measured with CUDA events on the context's stream. */
+int prt_b200_set_tris_dev(prt_b200 *ctx, const float *d_tris9, uint64_t n_tris, float *build_ms);
+
+/* nearest_hits<Tags...>(const std::vector<Ray>&) -- the member template every backend provides
+ * (CPU: intersect_cpu.hpp:20-43; OptiX: intersect_optix.hpp:64-119) and that the free function
+ * reaches through std::visit (nearest_hits_impl.hpp:28-36).  rays6: HOST pointer, n_rays records
+ * of 6 floats (origin, direction; 24-byte stride, core.hpp:19-22).  hits_out: HOST pointer to
+ * n_rays records laid out as `layout` describes (the caller's std::vector<HitReg<Tags...>>).
+ * Semantics are those of BVH2::nearest_tri (bvh.hpp:224-265): minimum t over all triangles that
+ * pass ray_box_intersect on their own AABB (bvh.hpp:195-222) and intersect_tri (core.hpp:27-65),
+ * negative t included, no tmax; t = +inf, valid = false, p = o + inf*d on a miss.  Fields the
+ * reference leaves indeterminate on a miss are written as u = v = 0, primitive_id = 0xFFFFFFFF. */
+int prt_b200_nearest_hits(prt_b200 *ctx, const float *rays6, uint64_t n_rays, uint32_t tag_mask,
+                          const prt_hit_layout *layout, void *hits_out);
+
+/* Device-resident traversal for device-timed measurement: rays and outputs live on the context's
+ * device.  *trace_ms (may be NULL) = device time of the traversal kernel(s), CUDA events on the
+ * context's stream.  Fields not in tag_mask are not written (and may be NULL). */
+int prt_b200_trace_dev(prt_b200 *ctx, const float *d_rays6, uint64_t n_rays, uint32_t tag_mask,
+                       const prt_soa_out *d_out, float *trace_ms);
+
+/* Same traversal, AoS records written on the device at d_hits (layout as for nearest_hits). */
+int prt_b200_trace_dev_aos(prt_b200 *ctx, const float *d_rays6, uint64_t n_rays,
+                           uint32_t tag_mask, const prt_hit_layout *layout, void *d_hits,
+                           float *trace_ms);
+
+/* Traversal knobs; opts == NULL restores the defaults. */
+int prt_b200_set_trace_opts(prt_b200 *ctx, const prt_trace_opts *opts);
+
+/* Instrumented traversal (never used in timed runs): per ray, counts[2i] = internal nodes
+ * fetched, counts[2i+1] = triangles tested; feeds the bytes/ray figure of the roofline
+ * (SURVEY.md 8d).  d_counts: device pointer to 2*n_rays uint32. */
+int prt_b200_trace_count_dev(prt_b200 *ctx, const float *d_rays6, uint64_t n_rays,
+                             uint32_t *d_counts);
+
+/* Introspection for tests and the bench. */
+uint64_t prt_b200_num_tris(const prt_b200 *ctx);
+uint64_t prt_b200_num_nodes(const prt_b200 *ctx);
+uint64_t prt_b200_bvh_bytes(const prt_b200 *ctx);      /* node array + triangle array on device */
+uint64_t prt_b200_launch_count(const prt_b200 *ctx);   /* kernels launched by this context so far */
+float prt_b200_last_build_ms(const prt_b200 *ctx);     /* device time of the last build */
+float prt_b200_last_trace_ms(const prt_b200 *ctx);     /* device time of the last traversal */
+/* Copies the built BVH back to the host for structural tests: nodes (64 B each), triangle records
+ * (48 B each).  Either pointer may be NULL. */
+int prt_b200_download_bvh(const prt_b200 *ctx, void *nodes_out, void *tris_out);
+
+const char *prt_b200_last_error(const prt_b200 *ctx); /* ctx may be NULL: last create() error */
+int prt_b200_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRT_B200_H */

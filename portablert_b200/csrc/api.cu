@@ -1,0 +1,345 @@
+// api.cu -- the extern "C" layer (include/prt_b200.h).  Host glue only: context life cycle,
+// grow-only device scratch, pinned double-buffered staging for the host-pointer entry points, CUDA
+// event timing.  No computation happens on the host and there is no CPU fallback.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "prt_ctx.h"
+
+using prt::fail;
+
+static thread_local std::string g_create_err;
+
+extern "C" {
+
+int prt_b200_abi_version(void) { return PRT_B200_ABI_VERSION; }
+
+int prt_b200_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError(); // clear the sticky "no device" error
+		return 0;
+	}
+	int ok = 0;
+	for (int d = 0; d < n; ++d) {
+		int major = 0;
+		if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess &&
+		    major == 10)
+			++ok;
+	}
+	return ok;
+}
+
+const char *prt_b200_last_error(const prt_b200 *c) {
+	return c ? c->err.c_str() : g_create_err.c_str();
+}
+
+int prt_b200_create(prt_b200 **out, int device) {
+	if (!out) {
+		g_create_err = "create: out == NULL";
+		return PRT_E_ARG;
+	}
+	*out = nullptr;
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+		cudaGetLastError();
+		g_create_err = "no CUDA device visible (this backend has no CPU fallback)";
+		return PRT_E_NO_DEVICE;
+	}
+	if (device < 0) {
+		if (const char *e = std::getenv("PRT_B200_DEVICE"))
+			device = std::atoi(e);
+	}
+	if (device < 0) {
+		for (int d = 0; d < n && device < 0; ++d) {
+			int major = 0;
+			cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d);
+			if (major == 10)
+				device = d;
+		}
+	}
+	int major = 0;
+	if (device < 0 || device >= n ||
+	    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess ||
+	    major != 10) {
+		g_create_err = "no compute-capability-10.x (sm_100a) device: kernels are built for B200 only";
+		return PRT_E_NO_DEVICE;
+	}
+	prt_b200 *c = new prt_b200();
+	c->device = device;
+	cudaError_t e = cudaSetDevice(device);
+	cudaDeviceProp prop{};
+	if (e == cudaSuccess)
+		e = cudaGetDeviceProperties(&prop, device);
+	if (e == cudaSuccess)
+		e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+	for (int k = 0; k < 2 && e == cudaSuccess; ++k)
+		e = cudaStreamCreateWithFlags(&c->copy_stream[k], cudaStreamNonBlocking);
+	if (e == cudaSuccess)
+		e = cudaEventCreate(&c->ev0);
+	if (e == cudaSuccess)
+		e = cudaEventCreate(&c->ev1);
+	for (int k = 0; k < 2 && e == cudaSuccess; ++k)
+		for (int j = 0; j < 2 && e == cudaSuccess; ++j)
+			e = cudaEventCreateWithFlags(&c->ev_chunk[k][j], cudaEventDisableTiming);
+	if (e != cudaSuccess) {
+		g_create_err = std::string("create: ") + cudaGetErrorString(e);
+		prt_b200_destroy(c);
+		return PRT_E_CUDA;
+	}
+	c->sm_count = prop.multiProcessorCount;
+	c->name = prop.name;
+	*out = c;
+	return PRT_OK;
+}
+
+void prt_b200_destroy(prt_b200 *c) {
+	if (!c)
+		return;
+	if (c->device >= 0)
+		cudaSetDevice(c->device);
+	if (c->stream)
+		cudaStreamSynchronize(c->stream);
+	prt::DevBuf *bufs[] = {&c->tris_raw, &c->nodes,    &c->trirecs,     &c->keys[0],     &c->keys[1],
+	                       &c->vals[0],  &c->vals[1],  &c->counts,      &c->totals,      &c->bounds,
+	                       &c->leaf_box, &c->node_box, &c->parent,      &c->leaf_parent, &c->flags,
+	                       &c->rays_dev[0], &c->rays_dev[1], &c->hits_dev[0], &c->hits_dev[1],
+	                       &c->counter};
+	for (auto *b : bufs)
+		b->release();
+	for (int k = 0; k < 2; ++k) {
+		c->rays_pin[k].release();
+		c->hits_pin[k].release();
+		if (c->copy_stream[k])
+			cudaStreamDestroy(c->copy_stream[k]);
+		for (int j = 0; j < 2; ++j)
+			if (c->ev_chunk[k][j])
+				cudaEventDestroy(c->ev_chunk[k][j]);
+	}
+	if (c->ev0)
+		cudaEventDestroy(c->ev0);
+	if (c->ev1)
+		cudaEventDestroy(c->ev1);
+	if (c->stream)
+		cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+int prt_b200_device_name(const prt_b200 *c, char *buf, size_t cap) {
+	if (!c || !buf || !cap)
+		return 0;
+	std::strncpy(buf, c->name.c_str(), cap - 1);
+	buf[cap - 1] = 0;
+	return (int)std::min(c->name.size(), cap - 1);
+}
+
+int prt_b200_set_trace_opts(prt_b200 *c, const prt_trace_opts *o) {
+	if (!c)
+		return PRT_E_ARG;
+	if (o)
+		c->opts = *o;
+	else
+		c->opts = prt_trace_opts{1, 1e-4f, 64.0f};
+	return PRT_OK;
+}
+
+static int timed_build(prt_b200 *c, const float *d_tris9, uint64_t n, float *ms) {
+	PRT_CUDA(c, cudaSetDevice(c->device));
+	PRT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+	int rc = prt::build_lbvh(c, d_tris9, n);
+	if (rc)
+		return rc;
+	PRT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+	PRT_CUDA(c, cudaStreamSynchronize(c->stream));
+	PRT_CUDA(c, cudaEventElapsedTime(&c->last_build_ms, c->ev0, c->ev1));
+	if (ms)
+		*ms = c->last_build_ms;
+	return PRT_OK;
+}
+
+int prt_b200_set_tris_dev(prt_b200 *c, const float *d_tris9, uint64_t n, float *build_ms) {
+	if (!c || (n && !d_tris9))
+		return fail(c, PRT_E_ARG, "set_tris_dev: NULL argument");
+	return timed_build(c, d_tris9, n, build_ms);
+}
+
+int prt_b200_set_tris(prt_b200 *c, const float *tris9, uint64_t n) {
+	if (!c || (n && !tris9))
+		return fail(c, PRT_E_ARG, "set_tris: NULL argument");
+	PRT_CUDA(c, cudaSetDevice(c->device));
+	if (n) {
+		PRT_CUDA(c, c->tris_raw.reserve(n * 36));
+		PRT_CUDA(c, cudaMemcpyAsync(c->tris_raw.p, tris9, n * 36, cudaMemcpyHostToDevice, c->stream));
+	}
+	return timed_build(c, c->tris_raw.as<float>(), n, nullptr);
+}
+
+static int check_layout(prt_b200 *c, uint32_t mask, const prt_hit_layout *l) {
+	if (!l || l->stride == 0)
+		return fail(c, PRT_E_ARG, "nearest_hits: NULL/empty hit layout");
+	struct {
+		uint32_t bit;
+		int32_t off;
+		int32_t size;
+	} f[] = {{PRT_TAG_UV, l->off_u, 4},    {PRT_TAG_UV, l->off_v, 4},  {PRT_TAG_T, l->off_t, 4},
+	         {PRT_TAG_PID, l->off_pid, 4}, {PRT_TAG_VALID, l->off_valid, 1},
+	         {PRT_TAG_P, l->off_px, 4},    {PRT_TAG_P, l->off_py, 4},  {PRT_TAG_P, l->off_pz, 4}};
+	for (auto &x : f) {
+		if (!(mask & x.bit))
+			continue;
+		if (x.off < 0 || (uint32_t)(x.off + x.size) > l->stride || (x.size == 4 && (x.off & 3)))
+			return fail(c, PRT_E_ARG, "nearest_hits: hit layout lacks a field the tag mask requests");
+	}
+	if (l->stride & 3) {
+		// 4-byte stores need 4-byte aligned records unless only `valid` is written
+		if (mask != PRT_TAG_VALID)
+			return fail(c, PRT_E_ARG, "nearest_hits: record stride must be a multiple of 4");
+	}
+	return PRT_OK;
+}
+
+static int timed_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask,
+                       const prt::TraceOut &out, uint32_t *d_counts, float *ms) {
+	PRT_CUDA(c, cudaSetDevice(c->device));
+	PRT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+	int rc = prt::launch_trace(c, d_rays6, n, mask, out, d_counts, c->stream);
+	if (rc)
+		return rc;
+	PRT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+	PRT_CUDA(c, cudaStreamSynchronize(c->stream));
+	PRT_CUDA(c, cudaEventElapsedTime(&c->last_trace_ms, c->ev0, c->ev1));
+	if (ms)
+		*ms = c->last_trace_ms;
+	return PRT_OK;
+}
+
+int prt_b200_trace_dev(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask,
+                       const prt_soa_out *o, float *trace_ms) {
+	if (!c || !o || (n && !d_rays6))
+		return fail(c, PRT_E_ARG, "trace_dev: NULL argument");
+	if (mask == 0 || mask > PRT_TAG_ALL)
+		return fail(c, PRT_E_ARG, "trace_dev: tag mask must be in 1..31");
+	if (n && (((mask & PRT_TAG_UV) && !o->uv) || ((mask & PRT_TAG_T) && !o->t) ||
+	          ((mask & PRT_TAG_PID) && !o->pid) || ((mask & PRT_TAG_P) && !o->p) ||
+	          ((mask & PRT_TAG_VALID) && !o->valid)))
+		return fail(c, PRT_E_ARG, "trace_dev: NULL output for a requested tag");
+	prt::TraceOut out;
+	out.soa = *o;
+	return timed_trace(c, d_rays6, n, mask, out, nullptr, trace_ms);
+}
+
+int prt_b200_trace_dev_aos(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask,
+                           const prt_hit_layout *layout, void *d_hits, float *trace_ms) {
+	if (!c || (n && (!d_rays6 || !d_hits)))
+		return fail(c, PRT_E_ARG, "trace_dev_aos: NULL argument");
+	if (mask == 0 || mask > PRT_TAG_ALL)
+		return fail(c, PRT_E_ARG, "trace_dev_aos: tag mask must be in 1..31");
+	if (int rc = check_layout(c, mask, layout))
+		return rc;
+	prt::TraceOut out;
+	out.aos = d_hits;
+	out.layout = *layout;
+	return timed_trace(c, d_rays6, n, mask, out, nullptr, trace_ms);
+}
+
+int prt_b200_trace_count_dev(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t *d_counts) {
+	if (!c || (n && (!d_rays6 || !d_counts)))
+		return fail(c, PRT_E_ARG, "trace_count_dev: NULL argument");
+	prt::TraceOut out;
+	return timed_trace(c, d_rays6, n, PRT_TAG_ALL, out, d_counts, nullptr);
+}
+
+// Host-pointer entry point.  Rays are cut into chunks; each chunk goes pageable -> pinned (host
+// memcpy) -> device (async H2D) -> traversal kernel writing the caller's AoS records -> pinned
+// (async D2H) -> the caller's buffer.  Two buffer sets alternate so the copies of chunk k+1
+// overlap the traversal of chunk k.
+int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t mask,
+                          const prt_hit_layout *layout, void *hits_out) {
+	if (!c || (n && (!rays6 || !hits_out)))
+		return fail(c, PRT_E_ARG, "nearest_hits: NULL argument");
+	if (mask == 0 || mask > PRT_TAG_ALL)
+		return fail(c, PRT_E_ARG, "nearest_hits: tag mask must be in 1..31");
+	if (int rc = check_layout(c, mask, layout))
+		return rc;
+	if (n == 0)
+		return PRT_OK;
+	PRT_CUDA(c, cudaSetDevice(c->device));
+
+	const uint64_t CH = std::min<uint64_t>(n, 1ull << 20);
+	const size_t ray_b = 24, hit_b = layout->stride;
+	for (int k = 0; k < 2; ++k) {
+		PRT_CUDA(c, c->rays_dev[k].reserve(CH * ray_b));
+		PRT_CUDA(c, c->hits_dev[k].reserve(CH * hit_b));
+		PRT_CUDA(c, c->rays_pin[k].reserve(CH * ray_b));
+		PRT_CUDA(c, c->hits_pin[k].reserve(CH * hit_b));
+	}
+	const uint64_t n_chunks = (n + CH - 1) / CH;
+	PRT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+	// software pipeline over chunks: stage(k) | trace(k-1) | drain(k-2)
+	for (uint64_t k = 0; k < n_chunks + 1; ++k) {
+		if (k < n_chunks) {
+			const int b = (int)(k & 1);
+			const uint64_t first = k * CH, cnt = std::min(CH, n - first);
+			if (k >= 2) {
+				// buffer set b was last used by chunk k-2: wait for its D2H, hand the hits over
+				PRT_CUDA(c, cudaEventSynchronize(c->ev_chunk[b][1]));
+				const uint64_t pf = (k - 2) * CH, pc = std::min(CH, n - pf);
+				std::memcpy(static_cast<char *>(hits_out) + pf * hit_b, c->hits_pin[b].p, pc * hit_b);
+			}
+			std::memcpy(c->rays_pin[b].p, rays6 + first * 6, cnt * ray_b);
+			PRT_CUDA(c, cudaMemcpyAsync(c->rays_dev[b].p, c->rays_pin[b].p, cnt * ray_b,
+			                            cudaMemcpyHostToDevice, c->stream));
+			prt::TraceOut out;
+			out.aos = c->hits_dev[b].p;
+			out.layout = *layout;
+			int rc = prt::launch_trace(c, c->rays_dev[b].as<float>(), cnt, mask, out, nullptr,
+			                           c->stream);
+			if (rc)
+				return rc;
+			PRT_CUDA(c, cudaMemcpyAsync(c->hits_pin[b].p, c->hits_dev[b].p, cnt * hit_b,
+			                            cudaMemcpyDeviceToHost, c->stream));
+			PRT_CUDA(c, cudaEventRecord(c->ev_chunk[b][1], c->stream));
+		}
+	}
+	PRT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+	// drain the last (up to) two chunks
+	const uint64_t first_pending = n_chunks >= 2 ? n_chunks - 2 : 0;
+	for (uint64_t k = first_pending; k < n_chunks; ++k) {
+		const int b = (int)(k & 1);
+		PRT_CUDA(c, cudaEventSynchronize(c->ev_chunk[b][1]));
+		const uint64_t pf = k * CH, pc = std::min(CH, n - pf);
+		std::memcpy(static_cast<char *>(hits_out) + pf * hit_b, c->hits_pin[b].p, pc * hit_b);
+	}
+	PRT_CUDA(c, cudaStreamSynchronize(c->stream));
+	PRT_CUDA(c, cudaEventElapsedTime(&c->last_trace_ms, c->ev0, c->ev1));
+	return PRT_OK;
+}
+
+uint64_t prt_b200_num_tris(const prt_b200 *c) { return c ? c->n_tris : 0; }
+uint64_t prt_b200_num_nodes(const prt_b200 *c) { return c ? c->n_nodes : 0; }
+uint64_t prt_b200_bvh_bytes(const prt_b200 *c) {
+	return c ? c->n_nodes * sizeof(prt::Node) + c->n_tris * sizeof(prt::TriRec) : 0;
+}
+uint64_t prt_b200_launch_count(const prt_b200 *c) { return c ? c->launches : 0; }
+float prt_b200_last_build_ms(const prt_b200 *c) { return c ? c->last_build_ms : 0.f; }
+float prt_b200_last_trace_ms(const prt_b200 *c) { return c ? c->last_trace_ms : 0.f; }
+
+int prt_b200_download_bvh(const prt_b200 *cc, void *nodes_out, void *tris_out) {
+	prt_b200 *c = const_cast<prt_b200 *>(cc);
+	if (!c)
+		return PRT_E_ARG;
+	PRT_CUDA(c, cudaSetDevice(c->device));
+	PRT_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (nodes_out && c->n_nodes)
+		PRT_CUDA(c, cudaMemcpy(nodes_out, c->nodes.p, c->n_nodes * sizeof(prt::Node),
+		                       cudaMemcpyDeviceToHost));
+	if (tris_out && c->n_tris)
+		PRT_CUDA(c, cudaMemcpy(tris_out, c->trirecs.p, c->n_tris * sizeof(prt::TriRec),
+		                       cudaMemcpyDeviceToHost));
+	return PRT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,132 @@
+// prt_ctx.h -- internal context shared by api.cu / build.cu / trace.cu (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/prt_b200.h"
+#include "prt_math.cuh"
+
+namespace prt {
+
+// Grow-only device buffer: the reference's GPU backends malloc/free on every call
+// (intersect_optix.hpp:73-116); here scratch survives across set_tris / nearest_hits calls so a
+// per-frame rebuild (config C5) never touches the allocator.
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	cudaError_t reserve(size_t bytes) {
+		if (bytes <= cap)
+			return cudaSuccess;
+		if (p)
+			cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = bytes + bytes / 8 + 256; // slack so slowly growing inputs do not realloc
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e == cudaSuccess)
+			cap = want;
+		return e;
+	}
+	void release() {
+		if (p)
+			cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+	template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct PinnedBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	cudaError_t reserve(size_t bytes) {
+		if (bytes <= cap)
+			return cudaSuccess;
+		if (p)
+			cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+		cudaError_t e = cudaMallocHost(&p, bytes);
+		if (e == cudaSuccess)
+			cap = bytes;
+		return e;
+	}
+	void release() {
+		if (p)
+			cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+	}
+};
+
+} // namespace prt
+
+struct prt_b200 {
+	int device = -1;
+	int sm_count = 0;
+	cudaStream_t stream = nullptr;
+	cudaStream_t copy_stream[2] = {nullptr, nullptr};
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaEvent_t ev_chunk[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+	std::string name;
+	std::string err;
+
+	// scene
+	uint64_t n_tris = 0;
+	uint64_t n_nodes = 0;
+	prt::DevBuf tris_raw;  // staged copy of the caller's 36-byte records (host entry point only)
+	prt::DevBuf nodes;     // prt::Node[n_nodes]
+	prt::DevBuf trirecs;   // prt::TriRec[n_tris]
+
+	// build scratch
+	prt::DevBuf keys[2], vals[2], counts, totals, bounds, leaf_box, node_box, parent, leaf_parent,
+	    flags;
+
+	// trace scratch
+	prt::DevBuf rays_dev[2], hits_dev[2], counter;
+	prt::PinnedBuf rays_pin[2], hits_pin[2];
+
+	prt_trace_opts opts{1, 1e-4f, 64.0f};
+
+	uint64_t launches = 0;
+	float last_build_ms = 0.f, last_trace_ms = 0.f;
+};
+
+namespace prt {
+
+inline int fail(prt_b200 *c, int code, const char *what, cudaError_t e = cudaSuccess) {
+	if (c) {
+		c->err = what;
+		if (e != cudaSuccess) {
+			c->err += ": ";
+			c->err += cudaGetErrorString(e);
+		}
+	}
+	return code;
+}
+
+#define PRT_CUDA(ctx, call)                                                                        \
+	do {                                                                                           \
+		cudaError_t e__ = (call);                                                                  \
+		if (e__ != cudaSuccess)                                                                    \
+			return prt::fail(ctx, e__ == cudaErrorMemoryAllocation ? PRT_E_OOM : PRT_E_CUDA,       \
+			                 #call, e__);                                                          \
+	} while (0)
+
+// build.cu
+int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n);
+// trace.cu
+struct TraceOut {
+	// SoA (aos == nullptr) or AoS (aos != nullptr)
+	prt_soa_out soa{};
+	void *aos = nullptr;
+	prt_hit_layout layout{};
+};
+int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, const TraceOut &out,
+                 uint32_t *d_counts, cudaStream_t stream);
+
+} // namespace prt

@@ -1,0 +1,244 @@
+// prt_math.cuh -- parity-critical arithmetic and BVH record types shared by build and traversal.
+//
+// Everything that decides `valid`, `primitive_id`, t, u, v replays the reference's float
+// operations in the reference's operand order with NO fused multiply-add:
+//   * ray_box_intersect  include/portableRT/bvh.hpp:195-222   -> prt::slab_ref
+//   * intersect_tri      include/portableRT/core.hpp:27-65    -> prt::moller_trumbore_ref
+//   * make_aabb          include/portableRT/bvh.hpp:28-37     -> prt::tri_lo / prt::tri_hi
+// On the device the *_rn intrinsics are used (ptxas never contracts them into FFMA); compiled for
+// the host (tests/emu only -- NOT a product path) plain operators are used and the build adds
+// -ffp-contract=off.
+#pragma once
+
+#include <cstdint>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define PRT_HD __host__ __device__ __forceinline__
+#else
+#define PRT_HD inline
+#endif
+
+namespace prt {
+
+#if defined(__CUDA_ARCH__)
+PRT_HD float fmul(float a, float b) { return __fmul_rn(a, b); }
+PRT_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
+PRT_HD float fsub(float a, float b) { return __fsub_rn(a, b); }
+PRT_HD float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+#else
+PRT_HD float fmul(float a, float b) { return a * b; }
+PRT_HD float fadd(float a, float b) { return a + b; }
+PRT_HD float fsub(float a, float b) { return a - b; }
+PRT_HD float fdiv(float a, float b) { return a / b; }
+#endif
+
+// std::min / std::max of the reference: (b<a)?b:a and (a<b)?b:a.  NaN-order-sensitive, unlike
+// fminf/fmaxf (which drop NaNs).
+PRT_HD float smin(float a, float b) { return (b < a) ? b : a; }
+PRT_HD float smax(float a, float b) { return (a < b) ? b : a; }
+
+// ---------------------------------------------------------------------------------------------
+// Device BVH records.
+//
+// Node (64 B, four 16-byte loads): a binary node that carries BOTH children's exact fp32 boxes, so
+// one fetch decides two subtrees and a leaf's own AABB test (the reference's per-leaf
+// ray_box_intersect) is done by its parent without touching the triangle.
+//   child < 0            : leaf, triangle record index = ~child
+//   child >= 0           : internal node index
+//   child == PRT_NO_CHILD: absent (single-triangle scene, bvh.hpp:165-181)
+struct __attribute__((aligned(16))) Node {
+	float lo0[3];
+	float hi0[3];
+	float lo1[3];
+	float hi1[3];
+	int32_t child0, child1;
+	uint32_t pad0, pad1;
+};
+static_assert(sizeof(Node) == 64, "Node must be 64 bytes");
+
+#define PRT_NO_CHILD ((int32_t)0x7fffffff)
+
+// Triangle record (48 B, three 16-byte loads), stored in Morton order: v0 and the two edges
+// exactly as intersect_tri computes them (core.hpp:33-35: edge = v1 - v0, v2 - v0 in binary32), plus
+// the caller's triangle index (= primitive_id).
+struct __attribute__((aligned(16))) TriRec {
+	float v0[3];
+	uint32_t prim;
+	float e1[3];
+	uint32_t pad1;
+	float e2[3];
+	uint32_t pad2;
+};
+static_assert(sizeof(TriRec) == 48, "TriRec must be 48 bytes");
+
+struct Box {
+	float lo[3], hi[3];
+};
+
+// make_aabb, bvh.hpp:28-37 (same nesting: min(a, min(b, c)))
+PRT_HD Box tri_box(const float *t9) {
+	Box b;
+#pragma unroll
+	for (int a = 0; a < 3; ++a) {
+		b.lo[a] = smin(t9[a], smin(t9[a + 3], t9[a + 6]));
+		b.hi[a] = smax(t9[a], smax(t9[a + 3], t9[a + 6]));
+	}
+	return b;
+}
+
+// extend_aabb, bvh.hpp:39-48
+PRT_HD Box box_union(const Box &a, const Box &b) {
+	Box r;
+#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		r.lo[k] = smin(a.lo[k], b.lo[k]);
+		r.hi[k] = smax(a.hi[k], b.hi[k]);
+	}
+	return r;
+}
+
+// Per-ray constants.  idir = 1.0f / d (bvh.hpp:199-201; the reference recomputes it per box, the
+// value is the same).
+struct RayC {
+	float o[3], d[3], idir[3];
+};
+
+PRT_HD RayC make_ray(const float *r6) {
+	RayC r;
+#pragma unroll
+	for (int a = 0; a < 3; ++a) {
+		r.o[a] = r6[a];
+		r.d[a] = r6[a + 3];
+		r.idir[a] = fdiv(1.0f, r6[a + 3]);
+	}
+	return r;
+}
+
+// ray_box_intersect, bvh.hpp:195-222.  Returns pass/fail exactly as the reference does and the
+// entry parameter tmin (bvh.hpp:210) for ordering and pruning.  Because fp32 subtraction and
+// multiplication are monotone, a box that contains another passes whenever the inner one does, so
+// applying this same arithmetic to the exact union boxes of internal nodes can never cull a
+// triangle the reference would accept.  The one exception is 0*inf = NaN (ray parallel to and
+// lying in a face plane of a box): there the reference's own verdict depends on its tree topology
+// and cannot be reproduced from any other tree -- see DESIGN.md "NaN corner cases".
+PRT_HD bool slab_ref(const RayC &r, const float *lo, const float *hi, float &tmin_out) {
+	float t1 = fmul(fsub(lo[0], r.o[0]), r.idir[0]);
+	float t2 = fmul(fsub(hi[0], r.o[0]), r.idir[0]);
+	float t3 = fmul(fsub(lo[1], r.o[1]), r.idir[1]);
+	float t4 = fmul(fsub(hi[1], r.o[1]), r.idir[1]);
+	float t5 = fmul(fsub(lo[2], r.o[2]), r.idir[2]);
+	float t6 = fmul(fsub(hi[2], r.o[2]), r.idir[2]);
+	float tmin = smax(smax(smin(t1, t2), smin(t3, t4)), smin(t5, t6));
+	float tmax = smin(smin(smax(t1, t2), smax(t3, t4)), smax(t5, t6));
+	tmin_out = tmin;
+	if (tmax < 0)
+		return false;
+	if (tmin > tmax)
+		return false;
+	return true;
+}
+
+// intersect_tri, core.hpp:27-65, on a TriRec (edges precomputed with the same subtraction).
+// Sums are left-to-right like the C++ expression a*b + c*d + e*f.
+PRT_HD bool moller_trumbore_ref(const RayC &r, const float *v0, const float *e1, const float *e2,
+                                float &t, float &u, float &v) {
+	float p0 = fsub(fmul(r.d[1], e2[2]), fmul(r.d[2], e2[1]));
+	float p1 = fsub(fmul(r.d[2], e2[0]), fmul(r.d[0], e2[2]));
+	float p2 = fsub(fmul(r.d[0], e2[1]), fmul(r.d[1], e2[0]));
+	float det = fadd(fadd(fmul(e1[0], p0), fmul(e1[1], p1)), fmul(e1[2], p2));
+	if (det == 0.0f)
+		return false;
+	float inv = fdiv(1.0f, det);
+	float s0 = fsub(r.o[0], v0[0]);
+	float s1 = fsub(r.o[1], v0[1]);
+	float s2 = fsub(r.o[2], v0[2]);
+	u = fmul(fadd(fadd(fmul(s0, p0), fmul(s1, p1)), fmul(s2, p2)), inv);
+	if (u < 0.0f || u > 1.0f)
+		return false;
+	float q0 = fsub(fmul(s1, e1[2]), fmul(s2, e1[1]));
+	float q1 = fsub(fmul(s2, e1[0]), fmul(s0, e1[2]));
+	float q2 = fsub(fmul(s0, e1[1]), fmul(s1, e1[0]));
+	v = fmul(fadd(fadd(fmul(r.d[0], q0), fmul(r.d[1], q1)), fmul(r.d[2], q2)), inv);
+	if (v < 0.0f || fadd(u, v) > 1.0f)
+		return false;
+	t = fmul(fadd(fadd(fmul(e2[0], q0), fmul(e2[1], q1)), fmul(e2[2], q2)), inv);
+	return true;
+}
+
+// Best-hit update.  The reference keeps the first-visited triangle among equal t (strict <,
+// bvh.hpp:247); its visit order is an artefact of its own SAH tree, so this backend defines a
+// deterministic, traversal-order-independent rule instead: lowest primitive_id among equal t.
+PRT_HD bool closer(float t, uint32_t prim, float t_best, uint32_t prim_best) {
+	return (t < t_best) || (t == t_best && prim < prim_best);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Morton codes: `bits` per axis (<= 21), x in the most significant position of each triple.
+PRT_HD uint64_t spread3(uint32_t v) { // 21 bits -> every third bit
+	uint64_t x = v & 0x1fffffull;
+	x = (x | x << 32) & 0x1f00000000ffffull;
+	x = (x | x << 16) & 0x1f0000ff0000ffull;
+	x = (x | x << 8) & 0x100f00f00f00f00full;
+	x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+	x = (x | x << 2) & 0x1249249249249249ull;
+	return x;
+}
+
+PRT_HD uint64_t morton3(uint32_t x, uint32_t y, uint32_t z) {
+	return (spread3(x) << 2) | (spread3(y) << 1) | spread3(z);
+}
+
+PRT_HD int clz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+	return __clzll((long long)x);
+#else
+	return x ? __builtin_clzll(x) : 64;
+#endif
+}
+PRT_HD int clz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+	return __clz((int)x);
+#else
+	return x ? __builtin_clz(x) : 32;
+#endif
+}
+
+// Karras 2012 delta: length of the common prefix of (key_i . i) and (key_j . j); -1 out of range.
+PRT_HD int karras_delta(const uint64_t *keys, int64_t n, int64_t i, int64_t j) {
+	if (j < 0 || j >= n)
+		return -1;
+	uint64_t a = keys[i], b = keys[j];
+	if (a != b)
+		return clz64(a ^ b);
+	return 64 + clz32((uint32_t)i ^ (uint32_t)j);
+}
+
+// One internal node of the Karras hierarchy over n sorted keys: children and their ranges.
+// left/right are encoded child references (>=0 internal, ~leaf for leaves).
+PRT_HD void karras_node(const uint64_t *keys, int64_t n, int64_t i, int32_t &left, int32_t &right) {
+	int d = (karras_delta(keys, n, i, i + 1) - karras_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+	int dmin = karras_delta(keys, n, i, i - d);
+	int64_t lmax = 2;
+	while (karras_delta(keys, n, i, i + lmax * d) > dmin)
+		lmax *= 2;
+	int64_t l = 0;
+	for (int64_t t = lmax / 2; t >= 1; t /= 2)
+		if (karras_delta(keys, n, i, i + (l + t) * d) > dmin)
+			l += t;
+	int64_t j = i + l * d;
+	int dnode = karras_delta(keys, n, i, j);
+	int64_t s = 0;
+	int64_t t = l;
+	do {
+		t = (t + 1) / 2;
+		if (karras_delta(keys, n, i, i + (s + t) * d) > dnode)
+			s += t;
+	} while (t > 1);
+	int64_t gamma = i + s * d + (d < 0 ? -1 : 0);
+	int64_t lo = i < j ? i : j, hi = i < j ? j : i;
+	left = (lo == gamma) ? ~(int32_t)gamma : (int32_t)gamma;
+	right = (hi == gamma + 1) ? ~(int32_t)(gamma + 1) : (int32_t)(gamma + 1);
+}
+
+} // namespace prt

@@ -1,0 +1,63 @@
+"""Structural checks of a built BVH (nodes (n,16) float32 view of 64-byte nodes, tris (n,12))."""
+import numpy as np
+
+NO_CHILD = 0x7FFFFFFF
+
+
+def check_bvh(nodes, trirecs, tris):
+    """Every triangle sits in exactly one leaf, every node is reached exactly once from the root,
+    triangle records replay intersect_tri's edges bit-for-bit, child boxes are the EXACT union of
+    what is below them.  Returns the tree depth."""
+    n = len(tris)
+    assert len(trirecs) == n
+    if n == 0:
+        assert len(nodes) == 0
+        return 0
+    prim = trirecs[:, 3].copy().view(np.uint32)
+    assert np.array_equal(np.sort(prim), np.arange(n, dtype=np.uint32)), "prims are not a permutation"
+    src = tris[prim]
+    assert np.array_equal(trirecs[:, 0:3], src[:, 0:3])
+    assert np.array_equal(trirecs[:, 4:7], src[:, 3:6] - src[:, 0:3])
+    assert np.array_equal(trirecs[:, 8:11], src[:, 6:9] - src[:, 0:3])
+    v = src.reshape(n, 3, 3)
+    leaf_lo, leaf_hi = v.min(1), v.max(1)
+
+    ch = nodes[:, 12:14].copy().view(np.int32)
+    box = nodes[:, :12]
+    n_nodes = len(nodes)
+    assert n_nodes == (1 if n == 1 else n - 1)
+    lo = np.full((n_nodes, 3), np.inf, np.float32)
+    hi = np.full((n_nodes, 3), -np.inf, np.float32)
+    seen_leaf = np.zeros(n, bool)
+    seen_node = np.zeros(n_nodes, bool)
+    # iterative post-order
+    depth = 0
+    stack = [(0, 0, 1)]
+    while stack:
+        node, state, d = stack.pop()
+        depth = max(depth, d)
+        if state == 0:
+            assert not seen_node[node]
+            seen_node[node] = True
+            stack.append((node, 1, d))
+            for c in ch[node]:
+                if c >= 0 and c != NO_CHILD:
+                    stack.append((int(c), 0, d + 1))
+        else:
+            for k, c in enumerate(ch[node]):
+                blo = box[node, 6 * k:6 * k + 3]
+                bhi = box[node, 6 * k + 3:6 * k + 6]
+                if c == NO_CHILD:
+                    continue
+                if c < 0:
+                    j = ~int(c)
+                    assert not seen_leaf[j]
+                    seen_leaf[j] = True
+                    elo, ehi = leaf_lo[j], leaf_hi[j]
+                else:
+                    elo, ehi = lo[c], hi[c]
+                assert np.array_equal(blo, elo) and np.array_equal(bhi, ehi), (node, k)
+                lo[node] = np.minimum(lo[node], elo)
+                hi[node] = np.maximum(hi[node], ehi)
+    assert seen_leaf.all() and seen_node.all()
+    return depth

@@ -1,0 +1,177 @@
+// TEST INFRASTRUCTURE ONLY -- host-side logic emulator for the CPU-only test suite.
+//
+// The product (libprt_b200.so) runs exclusively on the GPU and has no CPU path.  This file lets the
+// `-m "not gpu"` tests exercise, without a GPU, the exact source the kernels are built from:
+//   * prt::karras_node / prt::morton3 / prt::tri_box / prt::box_union  (prt_math.cuh)
+//   * prt::traverse<...>                                                (prt_traverse.cuh)
+// by driving them from sequential host loops (std::sort instead of the device radix sort, a
+// post-order walk instead of the atomic refit).  It is compiled by g++ into tests/emu/libprt_emu.so,
+// loaded only by tests/, and never by portablert_b200/.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "../../portablert_b200/csrc/prt_traverse.cuh"
+
+using namespace prt;
+
+namespace {
+struct Emu {
+	std::vector<Node> nodes;
+	std::vector<TriRec> tris;
+	uint64_t n = 0;
+};
+
+Box refit(Emu &e, const std::vector<Box> &leaf, int32_t ref) {
+	if (ref < 0)
+		return leaf[~ref];
+	Node &nd = e.nodes[ref];
+	Box b0 = refit(e, leaf, nd.child0);
+	Box b1 = refit(e, leaf, nd.child1);
+	for (int a = 0; a < 3; ++a) {
+		nd.lo0[a] = b0.lo[a];
+		nd.hi0[a] = b0.hi[a];
+		nd.lo1[a] = b1.lo[a];
+		nd.hi1[a] = b1.hi[a];
+	}
+	return box_union(b0, b1);
+}
+} // namespace
+
+extern "C" {
+
+void *emu_build(const float *tris9, uint64_t n, int bits) {
+	Emu *e = new Emu();
+	e->n = n;
+	if (n == 0)
+		return e;
+	float cmin[3] = {INFINITY, INFINITY, INFINITY}, cmax[3] = {-INFINITY, -INFINITY, -INFINITY};
+	for (uint64_t i = 0; i < n; ++i) {
+		Box b = tri_box(tris9 + 9 * i);
+		for (int a = 0; a < 3; ++a) {
+			float c = 0.5f * b.lo[a] + 0.5f * b.hi[a];
+			cmin[a] = fminf(cmin[a], c);
+			cmax[a] = fmaxf(cmax[a], c);
+		}
+	}
+	const float cells = (float)(1u << bits);
+	const uint32_t qmax = (1u << bits) - 1u;
+	std::vector<uint64_t> keys(n);
+	std::vector<uint32_t> idx(n);
+	for (uint64_t i = 0; i < n; ++i) {
+		Box b = tri_box(tris9 + 9 * i);
+		uint32_t q[3];
+		for (int a = 0; a < 3; ++a) {
+			float ext = cmax[a] - cmin[a];
+			float scale = (ext > 0.0f && ext < INFINITY) ? cells / ext : 0.0f;
+			float c = 0.5f * b.lo[a] + 0.5f * b.hi[a];
+			float x = (c - cmin[a]) * scale;
+			q[a] = (x > 0.0f) ? (uint32_t)fminf(x, (float)qmax) : 0u;
+		}
+		keys[i] = morton3(q[0], q[1], q[2]);
+		idx[i] = (uint32_t)i;
+	}
+	std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+	std::vector<uint64_t> skeys(n);
+	std::vector<Box> leaf(n);
+	e->tris.resize(n);
+	for (uint64_t j = 0; j < n; ++j) {
+		const float *t = tris9 + 9ull * idx[j];
+		skeys[j] = keys[idx[j]];
+		leaf[j] = tri_box(t);
+		TriRec &r = e->tris[j];
+		std::memset(&r, 0, sizeof r);
+		for (int a = 0; a < 3; ++a) {
+			r.v0[a] = t[a];
+			r.e1[a] = t[3 + a] - t[a];
+			r.e2[a] = t[6 + a] - t[a];
+		}
+		r.prim = idx[j];
+	}
+	if (n == 1) {
+		e->nodes.resize(1);
+		Node &nd = e->nodes[0];
+		std::memset(&nd, 0, sizeof nd);
+		for (int a = 0; a < 3; ++a) {
+			nd.lo0[a] = leaf[0].lo[a];
+			nd.hi0[a] = leaf[0].hi[a];
+			nd.lo1[a] = INFINITY;
+			nd.hi1[a] = -INFINITY;
+		}
+		nd.child0 = ~0;
+		nd.child1 = PRT_NO_CHILD;
+		return e;
+	}
+	e->nodes.resize(n - 1);
+	std::memset(e->nodes.data(), 0, (n - 1) * sizeof(Node));
+	for (int64_t i = 0; i < (int64_t)n - 1; ++i) {
+		int32_t l, r;
+		karras_node(skeys.data(), (int64_t)n, i, l, r);
+		e->nodes[i].child0 = l;
+		e->nodes[i].child1 = r;
+	}
+	refit(*e, leaf, 0);
+	return e;
+}
+
+void emu_free(void *h) { delete static_cast<Emu *>(h); }
+uint64_t emu_num_nodes(void *h) { return static_cast<Emu *>(h)->nodes.size(); }
+void emu_download(void *h, void *nodes, void *tris) {
+	Emu *e = static_cast<Emu *>(h);
+	if (nodes && !e->nodes.empty())
+		std::memcpy(nodes, e->nodes.data(), e->nodes.size() * sizeof(Node));
+	if (tris && !e->tris.empty())
+		std::memcpy(tris, e->tris.data(), e->tris.size() * sizeof(TriRec));
+}
+// load an externally built tree (e.g. one downloaded from the GPU) for host-side checking
+void *emu_load(const void *nodes, uint64_t n_nodes, const void *tris, uint64_t n_tris) {
+	Emu *e = new Emu();
+	e->n = n_tris;
+	e->nodes.resize(n_nodes);
+	e->tris.resize(n_tris);
+	if (n_nodes)
+		std::memcpy(e->nodes.data(), nodes, n_nodes * sizeof(Node));
+	if (n_tris)
+		std::memcpy(e->tris.data(), tris, n_tris * sizeof(TriRec));
+	return e;
+}
+
+// SoA outputs like the device entry point; counts (2 per ray) may be NULL.  anyhit=1 emulates the
+// `valid`-only specialisation.
+void emu_trace(void *h, const float *rays6, uint64_t n, int prune, float slack_rel, float slack_ulps,
+               int anyhit, float *t, float *u, float *v, uint32_t *pid, uint8_t *valid, float *p,
+               uint32_t *counts) {
+	Emu *e = static_cast<Emu *>(h);
+	TraverseOpts o{prune, slack_rel, slack_ulps};
+	for (uint64_t i = 0; i < n; ++i) {
+		RayC r = make_ray(rays6 + 6 * i);
+		Hit hit;
+		if (anyhit)
+			traverse<true, false, false, false>(e->nodes.data(), e->tris.data(), e->n, r, o, hit);
+		else
+			traverse<false, true, true, true>(e->nodes.data(), e->tris.data(), e->n, r, o, hit);
+		if (t)
+			t[i] = hit.t;
+		if (u)
+			u[i] = hit.u;
+		if (v)
+			v[i] = hit.v;
+		if (pid)
+			pid[i] = hit.prim;
+		if (valid)
+			valid[i] = hit.t < INFINITY;
+		if (p) {
+			p[3 * i] = r.o[0] + hit.t * r.d[0];
+			p[3 * i + 1] = r.o[1] + hit.t * r.d[1];
+			p[3 * i + 2] = r.o[2] + hit.t * r.d[2];
+		}
+		if (counts) {
+			counts[2 * i] = hit.n_nodes;
+			counts[2 * i + 1] = hit.n_tris;
+		}
+	}
+}
+
+} // extern "C"

@@ -1,0 +1,125 @@
+"""CPU-only check of the kernel SOURCE: prt_math.cuh / prt_traverse.cuh driven by host loops
+(tests/emu) must reproduce the oracle.  This validates the parity logic (reference arithmetic,
+ordered descent, pruning slack, tie rule, any-hit) before any GPU time is spent; the real
+kernels are checked by the -m gpu tests."""
+import numpy as np
+import pytest
+
+import parity
+from bvhcheck import check_bvh
+from conftest import golden
+from portablert_b200 import scenes
+
+
+def _cases():
+    g = np.random.default_rng(2)
+    blob = scenes.blob(48, 48)
+    lo, hi = blob.reshape(-1, 3).min(0), blob.reshape(-1, 3).max(0)
+    soup = (g.random((1500, 3, 3), dtype=np.float32) * 2 - 1)
+    soup = (soup[:, :1] + (soup - soup[:, :1]) * np.float32(0.3)).reshape(-1, 9).astype(np.float32)
+    hf = scenes.heightfield(frame=3, nx=40, nz=30)
+    return {
+        "kat": (scenes.KAT_TRI, scenes.c1_rays(4000)),
+        "blob_primary": (blob, scenes.pinhole_rays(96, 64)),
+        "blob_incoherent": (blob, scenes.incoherent_rays(6000, lo - 0.05, hi + 0.05, 5)),
+        "soup_negative_t": (soup, scenes.incoherent_rays(6000, [-1] * 3, [1] * 3, 6)),
+        "heightfield": (hf, scenes.camera_rays(80, 60, (10, 6, -4), (10, 0, 5))),
+        "interior": (scenes.interior(6000), scenes.camera_rays(80, 60, (2, 6, 3), (28, 4, 15))),
+        "duplicates": (np.repeat(scenes.blob(6, 6), 5, axis=0), scenes.pinhole_rays(48, 48)),
+    }
+
+
+CASES = _cases()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_emulated_kernels_match_oracle(name, oracle, emu):
+    tris, rays = CASES[name]
+    oracle.build(tris)
+    ref = oracle.trace(rays, visits=True)
+    for bits in (10, 21):
+        emu.build(tris, bits)
+        exact = emu.trace(rays, prune=0)
+        rep = parity.compare(ref, exact, tris, rays, oracle)
+        parity.assert_parity(rep)
+        assert rep["t_bitexact"]
+        # unpruned traversal tests exactly the triangles whose own AABB the reference tests
+        # (rays with a zero direction component aside: 0*inf NaNs make the reference's box test
+        # order- and topology-dependent, see test_nan_corner_cases)
+        gen = ~(rays[:, 3:6] == 0).any(1)
+        assert np.array_equal(exact["counts"][gen, 1], ref["visits"][gen, 1])
+        pruned = emu.trace(rays, prune=1)
+        for k in ("t", "u", "v", "pid", "valid"):
+            assert np.array_equal(pruned[k], exact[k], equal_nan=True), (name, k)
+        assert pruned["counts"][:, 0].sum() <= exact["counts"][:, 0].sum()
+        any_ = emu.trace(rays, anyhit=True)
+        assert np.array_equal(any_["valid"], ref["valid"])
+
+
+def test_emulated_tree_structure(emu):
+    for tris in (scenes.KAT_TRI, scenes.blob(20, 20), np.repeat(scenes.KAT_TRI, 64, axis=0),
+                 scenes.heightfield(0, 30, 20)):
+        for bits in (10, 16, 21):
+            emu.build(tris, bits)
+            nodes, recs = emu.download()
+            depth = check_bvh(nodes, recs, tris)
+            assert depth <= 96
+
+
+def test_emulated_golden_bunny_and_soup(emu, oracle):
+    for name in ("bunny.npz", "soup.npz"):
+        g = golden(name)
+        emu.build(g["tris"], 16)
+        got = emu.trace(g["rays"])
+        rep = parity.compare(parity.from_structured(g["hits"]), got, g["tris"], g["rays"], oracle)
+        parity.assert_parity(rep)
+        assert rep["t_bitexact"]
+
+
+def test_tie_rule_is_lowest_primitive_id(emu):
+    """Documented deviation (SURVEY 8c rule 2 / 9.7): among equal t the reference keeps the first
+    triangle its own DFS visits; this backend keeps the lowest primitive_id."""
+    g = golden("kat.npz")
+    names = list(g["names"])
+    offs = g["tri_offsets"]
+    for nm, want in (("tie_two_identical", 0), ("tie_far_near_near", 1)):
+        k = names.index(nm)
+        emu.build(g["tris"][offs[k]:offs[k + 1]], 10)
+        got = emu.trace(g["rays"][k][None])
+        assert got["pid"][0] == want and got["t"][0] == g["hits"][k]["t"]
+
+
+def test_nan_corner_cases_are_confined_and_topology_dependent(emu, oracle):
+    """Rays lying IN a face plane of a triangle's AABB and parallel to it make the reference's
+    slab test produce 0*inf = NaN; its std::min/max chain is then order-sensitive (bvh.hpp:210-211)
+    and whether a triangle is even reached depends on the reference's own SAH topology: the
+    reference disagrees with its OWN per-triangle rule (oracle_brute) there, so no other tree can
+    reproduce it.  This documents the exception class: every disagreement with the reference sits
+    on a ray with an exactly-zero direction component whose origin coordinate on that axis equals
+    a triangle vertex coordinate; all other rays of the same (deliberately grid-aligned) scene are
+    bit-exact."""
+    g = np.random.default_rng(9)
+    q = np.float32(0.125)
+    tris = (np.round((g.random((600, 9), dtype=np.float32) * 2 - 1) / q) * q).astype(np.float32)
+    o = (np.round((g.random((8000, 3), dtype=np.float32) * 2 - 1) / q) * q).astype(np.float32)
+    d = g.standard_normal((8000, 3)).astype(np.float32)
+    ax = g.integers(0, 3, 8000)
+    zero = g.random(8000) < 0.5  # half the rays get one exactly-zero direction component
+    d[zero, ax[zero]] = 0.0
+    rays = np.concatenate([o, d], 1)
+    oracle.build(tris)
+    ref = oracle.trace(rays)
+    brute = oracle.brute(tris, rays)
+    own_rule_breaks = (ref["valid"] != brute["valid"]) | (ref["valid"] & (ref["t"] != brute["t"]))
+    assert own_rule_breaks.sum() > 0 and not own_rule_breaks[~zero].any()
+    emu.build(tris, 16)
+    for prune in (0, 1):
+        got = emu.trace(rays, prune=prune)
+        bad = (got["valid"] != ref["valid"]) | (ref["valid"] & (got["t"] != ref["t"]))
+        assert not bad[~zero].any()
+        gen = {k: v[~zero] for k, v in got.items() if k != "counts"}
+        rgen = {k: v[~zero] for k, v in ref.items()}
+        parity.assert_parity(parity.compare(rgen, gen, tris, rays[~zero], oracle))
+        print(f"prune={prune}: NaN-class disagreements with the reference {int(bad.sum())} of "
+              f"{int(zero.sum())} zero-component rays; reference vs its own rule "
+              f"{int(own_rule_breaks.sum())}")
