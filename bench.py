@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- device-timed Mrays/s of nearest_hits (+ BVH build Mtris/s) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c3|c4|c5] [--impl reference]
+
+One JSON line on stdout (rank 0).  A "step" is one nearest_hits pass over the whole ray batch of
+the workload.  Default workload = BASELINE.json configs[1] (C2): synthetic 69 192-triangle
+bunny-scale mesh, 1920x1080 coherent primary rays, all five filter tags (FullHitReg).
+
+  value       whole-job Mrays/s, rays resident in HBM, SoA outputs in HBM; per-step device time
+              from CUDA events on the stream the traversal kernel runs on (taken by the library
+              around the launch), L2 flushed between steps, max over ranks
+  e2e         the same metric through the reference-facing host API (host ray buffer in, host
+              HitReg records out: H2D + kernel + D2H inside the timed region)
+  roofline    the traversal kernel against the measured HBM peak (and the L2 read bandwidth
+              measured on the box), from ALGORITHMIC bytes per ray counted by the instrumented
+              kernel: 24 (ray) + 64 * nodes fetched + 64 * triangles tested + output bytes
+  cpu_baseline  the unmodified reference CPU backend (oracle/_ref) on the box's host cores
+  --impl reference  times only that CPU reference and prints the same line shape
+
+N > 1 (torchrun, one rank per GPU): rank 0's triangles are NCCL-broadcast, every rank builds the
+identical BVH, the ray batch is N x the single-GPU batch (weak scaling: N frames, rank r traces the
+r-th contiguous slice), hits stay in ray order and are NCCL-gathered to rank 0 in the e2e leg.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+# ------------------------------------------------------------------------------------------------
+def workload(name: str, frame: int = 0):
+    """-> (tris (N,9) f32, rays (R,6) f32, mask, description)"""
+    from portablert_b200 import hitreg, scenes
+    if name == "c2":
+        tris = scenes.blob()
+        # frame k > 0 moves the camera slightly so that N-GPU batches are N distinct frames
+        rays = scenes.pinhole_rays(1920, 1080, cam=(0.002 * frame, 0.0, -0.3))
+        return tris, rays, hitreg.ALL, ("C2: 69192-tri displaced-sphere mesh, 1920x1080 pinhole "
+                                        "primary rays, tags uv,t,primitive_id,p,valid")
+    if name == "c3":
+        tris = scenes.interior()
+        rays = scenes.camera_rays(3840, 2160, (2 + 0.01 * frame, 6, 3), (28, 4, 15))
+        return tris, rays, hitreg.ALL, ("C3: %d-tri interior, 3840x2160 primary rays, all tags"
+                                        % len(tris))
+    if name == "c5":
+        tris = scenes.heightfield(frame)
+        rays = scenes.camera_rays(3840, 2160, (10, 6, -4), (10, 0, 5))[:8_000_000]
+        return tris, rays, hitreg.T | hitreg.VALID, "C5: 1M-tri heightfield, 8M primary rays, t+valid"
+    if name == "c4":
+        n_s = int(os.environ.get("PRT_BENCH_C4_SPHERES", "10000"))
+        n_r = int(os.environ.get("PRT_BENCH_C4_RAYS", "100000000"))
+        tris = scenes.sphere_field(n_s)
+        lo, hi = tris.reshape(-1, 3).min(0), tris.reshape(-1, 3).max(0)
+        rays = scenes.incoherent_rays(n_r, lo, hi, seed=4 + frame)
+        return tris, rays, hitreg.T | hitreg.PID, ("C4: %d-tri sphere field, %d incoherent rays, "
+                                                   "t+primitive_id" % (len(tris), n_r))
+    raise SystemExit(f"unknown config {name}")
+
+
+class ClockSampler:
+    """SM clock and throttle reasons sampled through NVML DURING the timed region (a thread
+    polling every ~2 ms; nvidia-smi's 100 ms floor cannot see a millisecond-scale region)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.sm, self.reasons, self.mx = [], set(), None
+        self._stop = threading.Event()
+        self.thread = None
+        self.err = None
+
+    def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except Exception:
+                    pass
+            self.h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = nv
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        except Exception as e:  # no NVML: say so in the JSON instead of inventing numbers
+            self.err = repr(e)
+        return self
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            except Exception as e:
+                self.err = repr(e)
+                break
+            try:
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception as e:
+                self.err = "reasons: " + repr(e)
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop.set()
+        if self.thread:
+            self.thread.join(timeout=1.0)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": ["unavailable: %s" % self.err]}
+        out = {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.mx,
+               "reasons": sorted(self.reasons), "samples": len(self.sm)}
+        if self.err:
+            out["sampler_error"] = self.err
+        return out
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+OUT_BYTES = {1: 8, 2: 4, 4: 4, 8: 12, 16: 1}
+
+
+def out_bytes(mask):
+    return sum(b for bit, b in OUT_BYTES.items() if mask & bit)
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(tris, rays, mask, budget_s=25.0, steps=1, warmup=0):
+    """Time the unmodified reference CPU backend (oracle/_ref; test infrastructure, used here as
+    the reported baseline only) on a bounded sample of the workload."""
+    from oracle import Reference
+    ref = Reference()
+    b_s = ref.set_tris(tris)
+    # bounded sample: a strided subset keeps the image-space mix of hit and miss rays
+    probe = rays[:: max(1, len(rays) // 20000)][:20000]
+    ref.nearest_hits(probe, mask, keep=False)
+    rate = len(probe) / max(ref.last_trace_s, 1e-6)
+    n = int(min(len(rays), max(20000, rate * budget_s / max(1, steps + warmup))))
+    stride = max(1, len(rays) // n)
+    sample = np.ascontiguousarray(rays[::stride])
+    times = []
+    for k in range(warmup + steps):
+        ref.nearest_hits(sample, mask, keep=False)
+        if k >= warmup:
+            times.append(ref.last_trace_s)
+    s = float(np.mean(times))
+    what = ("all %d rays" % len(rays)) if stride == 1 else \
+        ("every %d-th ray (%d of %d)" % (stride, len(sample), len(rays)))
+    return {
+        "value": len(sample) / s / 1e6, "unit": "Mrays/s", "cores": ref.threads, "kind": "reference",
+        "sample": f"{what}; set_tris on all {len(tris)} tris (1 thread)",
+        "build_mtris_s": len(tris) / b_s / 1e6, "build_s": b_s, "trace_s": s,
+        "cpu": ref.device_name(), "n_sample": int(len(sample)),
+    }
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    tris, rays, mask, desc = workload(args.config)
+    cb = cpu_reference(tris, rays, mask, budget_s=60.0, steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": "nearest_hits throughput", "value": cb["value"],
+        "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": cb["trace_s"] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "tag_mask": mask},
+        "build_mtris_s": cb["build_mtris_s"],
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", default="c2")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-mask", action="store_true", help="also time all 31 tag masks")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import portablert_b200 as prt
+    from portablert_b200 import hitreg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    backend = prt.CUDABackend(device=local)
+    assert backend.is_available(), "bench.py needs a compute-capability-10.x GPU (no CPU fallback)"
+    prt.select_backend(backend)
+
+    # ---- inputs: rank 0 owns the scene; triangles are broadcast, each rank gets its ray slice
+    tris, rays, mask, desc = workload(args.config, frame=rank)
+    if world > 1:
+        d_tris = torch.from_numpy(tris).to(dev) if rank == 0 else torch.empty(tris.shape, device=dev)
+        dist.broadcast(d_tris, src=0)  # 36*N bytes over NVLink
+    else:
+        d_tris = torch.from_numpy(tris).to(dev)
+    d_rays = torch.from_numpy(rays).to(dev)
+    n_rays, n_tris = len(rays), len(tris)
+    uv = torch.empty(n_rays, 2, device=dev)
+    t = torch.empty(n_rays, device=dev)
+    pid = torch.empty(n_rays, dtype=torch.int32, device=dev)
+    p = torch.empty(n_rays, 3, device=dev)
+    valid = torch.empty(n_rays, dtype=torch.uint8, device=dev)
+    outs = dict(uv=uv.data_ptr() if mask & 1 else 0, t=t.data_ptr() if mask & 2 else 0,
+                pid=pid.data_ptr() if mask & 4 else 0, p=p.data_ptr() if mask & 8 else 0,
+                valid=valid.data_ptr() if mask & 16 else 0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def l2_flush():
+        flush.zero_()
+        torch.cuda.synchronize()
+
+    # ---- build (set_tris on device-resident triangles), timed by the library's own CUDA events
+    build_ms = []
+    for k in range(args.warmup + args.steps):
+        l2_flush()
+        ms = backend.set_tris_dev(d_tris.data_ptr(), n_tris)
+        if k >= args.warmup:
+            build_ms.append(ms)
+    build_launches = None
+
+    # ---- traversal: W warm-up + exactly K timed steps
+    for _ in range(args.warmup):
+        l2_flush()
+        backend.trace_dev(d_rays.data_ptr(), n_rays, mask, **outs)
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    barrier()
+    launches0 = backend.launch_count
+    wall0 = time.perf_counter()
+    step_ms = []
+    for _ in range(args.steps):
+        l2_flush()
+        step_ms.append(backend.trace_dev(d_rays.data_ptr(), n_rays, mask, **outs))
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = backend.launch_count - launches0
+    clocks = sampler.stop() if sampler else None
+    dev_ms = float(np.sum(step_ms))
+    if world > 1:
+        tt = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms_max = float(tt.item())
+        tb = torch.tensor([float(np.mean(build_ms))], device=dev, dtype=torch.float64)
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        build_ms_mean = float(tb.item())
+    else:
+        dev_ms_max = dev_ms
+        build_ms_mean = float(np.mean(build_ms))
+    ms_per_step = dev_ms_max / args.steps
+    total_rays = n_rays * world
+    value = total_rays / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e: the reference-facing call with HOST buffers (H2D + kernel + D2H in the timed region)
+    h_rays = rays
+    for _ in range(2):
+        backend.nearest_hits(h_rays, mask)
+    barrier()
+    e2e_t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        hits = backend.nearest_hits(h_rays, mask)
+        if world > 1:  # hits return to rank 0 in ray order
+            d_h = torch.from_numpy(hits.view(np.uint8).reshape(n_rays, -1)).to(dev)
+            gl = [torch.empty_like(d_h) for _ in range(world)] if rank == 0 else None
+            dist.gather(d_h, gl, dst=0)
+    barrier()
+    e2e_s = (time.perf_counter() - e2e_t0) / e2e_steps
+    if world > 1:
+        te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+    stride = hitreg.layout(mask)[0]
+    e2e = {"value": total_rays / e2e_s / 1e6, "unit": "Mrays/s",
+           "h2d_bytes_per_step": 24 * total_rays, "d2h_bytes_per_step": stride * total_rays,
+           "ms_per_step": e2e_s * 1e3, "api": "prt_b200_nearest_hits (host rays -> host HitReg AoS)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the traversal kernel (rank 0's slice)
+    cnt = torch.zeros(n_rays, 2, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    backend.trace_count_dev(d_rays.data_ptr(), n_rays, cnt.data_ptr())
+    c = cnt.to(torch.float64).mean(0).cpu().numpy()
+    nodes_per_ray, tris_per_ray = float(c[0]), float(c[1])
+    bytes_per_ray = 24 + 64 * nodes_per_ray + 64 * tris_per_ray + out_bytes(mask)
+    kern_ms = float(np.mean(step_ms))
+    achieved = n_rays * bytes_per_ray / (kern_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peaks()
+    l2_gbs = backend.read_bandwidth(32 << 20, 50)
+    hbm_read_gbs = backend.read_bandwidth(2 << 30, 3)
+    compulsory = n_rays * (24 + out_bytes(mask)) + backend.bvh_bytes
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.config)
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": traffic, "peak_source": peak_src, "kernel": "prt::k_trace<mask=%d,SoA>" % mask,
+        "kernel_ms": kern_ms, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
+        "tris_per_ray": tris_per_ray, "l2_read_gbs_measured": l2_gbs,
+        "hbm_read_gbs_measured": hbm_read_gbs, "frac_of_l2": achieved / l2_gbs,
+        "compulsory_bytes": compulsory,
+        "compulsory_frac_of_hbm": compulsory / (kern_ms * 1e-3) / 1e9 / peak,
+        "note": "BVH (%.1f MB) is L2-resident: fetched bytes are served by L1/L2, so the HBM "
+                "fraction can exceed the DRAM traffic; frac_of_l2 is the binding roofline" %
+                (backend.bvh_bytes / 1e6),
+    }
+    build_bytes_per_tri = 36 + 36 + 12 + (6 if n_tris <= (1 << 22) else 8) * (8 + 24) + 36 + 64 + 32 \
+        + 2 * 64 + 64
+    build = {"mtris_s": n_tris / (build_ms_mean * 1e-3) / 1e6, "ms": build_ms_mean,
+             "bytes_per_tri": build_bytes_per_tri,
+             "achieved_gbs": n_tris * build_bytes_per_tri / (build_ms_mean * 1e-3) / 1e9,
+             "frac_of_hbm": n_tris * build_bytes_per_tri / (build_ms_mean * 1e-3) / 1e9 / peak}
+
+    per_mask = None
+    if args.per_mask:
+        per_mask = {}
+        for combo in hitreg.TAG_COMBOS:
+            m = hitreg.mask_of(combo)
+            o = dict(uv=uv.data_ptr() if m & 1 else 0, t=t.data_ptr() if m & 2 else 0,
+                     pid=pid.data_ptr() if m & 4 else 0, p=p.data_ptr() if m & 8 else 0,
+                     valid=valid.data_ptr() if m & 16 else 0)
+            ts = []
+            for k in range(6):
+                l2_flush()
+                ms = backend.trace_dev(d_rays.data_ptr(), n_rays, m, **o)
+                if k >= 2:
+                    ts.append(ms)
+            per_mask["_".join(combo)] = n_rays / (np.mean(ts) * 1e-3) / 1e6
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_reference(tris, rays, mask, budget_s=20.0)
+        except Exception as e:  # the checker is optional equipment for the bench
+            cpu = {"unavailable": str(e)}
+
+    line = {
+        "metric": "nearest_hits throughput", "value": value, "unit": "Mrays/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": desc, "rays_per_gpu": n_rays, "tris": n_tris, "tag_mask": mask,
+                   "l2": "flushed between timed steps (256 MiB memset)",
+                   "multi_gpu": "tris NCCL-broadcast, BVH built on every rank, rank r traces "
+                                "frame r (contiguous slice), hits gathered to rank 0 in e2e"},
+        "build_mtris_s": build["mtris_s"], "build": build,
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu,
+        "wall_s_timed_region": wall, "device": backend.device_name(),
+    }
+    if per_mask:
+        line["per_mask_mrays_s"] = per_mask
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

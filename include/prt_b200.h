@@ -134,6 +134,10 @@ float prt_b200_last_trace_ms(const prt_b200 *ctx);     /* device time of the las
  * (48 B each).  Either pointer may be NULL. */
 int prt_b200_download_bvh(const prt_b200 *ctx, void *nodes_out, void *tris_out);
 
+/* Roofline denominators measured on the box: read bandwidth (GB/s) of `bytes` of device memory
+ * re-read `iters` times by a persistent grid (bytes << L2 size: L2 bandwidth; >> L2: HBM). */
+int prt_b200_read_bandwidth(prt_b200 *ctx, uint64_t bytes, int iters, float *gbs);
+
 const char *prt_b200_last_error(const prt_b200 *ctx); /* ctx may be NULL: last create() error */
 int prt_b200_abi_version(void);
 

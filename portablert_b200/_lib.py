@@ -52,6 +52,7 @@ SYMBOLS = {
     "prt_b200_last_build_ms": (C.c_float, [C.c_void_p]),
     "prt_b200_last_trace_ms": (C.c_float, [C.c_void_p]),
     "prt_b200_download_bvh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "prt_b200_read_bandwidth": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
     "prt_b200_last_error": (C.c_char_p, [C.c_void_p]),
 }
 

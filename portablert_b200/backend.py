@@ -147,6 +147,12 @@ class CUDABackend(Backend):
         o = TraceOpts(int(prune), float(slack_rel), float(slack_ulps))
         self._check(lib().prt_b200_set_trace_opts(self._h, C.byref(o)))
 
+    def read_bandwidth(self, nbytes: int, iters: int = 20) -> float:
+        self._need()
+        g = C.c_float()
+        self._check(lib().prt_b200_read_bandwidth(self._h, int(nbytes), int(iters), C.byref(g)))
+        return g.value
+
     # --- introspection --------------------------------------------------------------------------
     @property
     def num_tris(self):
@@ -173,10 +179,10 @@ class CUDABackend(Backend):
         return lib().prt_b200_last_trace_ms(self._h)
 
     def download_bvh(self):
-        """-> (nodes (n_nodes,16) float32 view of the 64-byte nodes, tris (n_tris,12) float32)."""
+        """-> (nodes (n_nodes,16) float32 view of the 64-byte nodes, tris (n_tris,16) float32: the 64-byte records)."""
         self._need()
         nodes = np.zeros((self.num_nodes, 16), np.float32)
-        tris = np.zeros((self.num_tris, 12), np.float32)
+        tris = np.zeros((self.num_tris, 16), np.float32)
         self._check(lib().prt_b200_download_bvh(self._h, nodes.ctypes.data, tris.ctypes.data))
         return nodes, tris
 

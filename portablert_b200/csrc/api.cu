@@ -2,6 +2,7 @@
 // grow-only device scratch, pinned double-buffered staging for the host-pointer entry points, CUDA
 // event timing.  No computation happens on the host and there is no CPU fallback.
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -91,6 +92,10 @@ int prt_b200_create(prt_b200 **out, int device) {
 		return PRT_E_CUDA;
 	}
 	c->sm_count = prop.multiProcessorCount;
+	if (const char *e = std::getenv("PRT_B200_FAST_BOXES"))
+		c->fast_boxes = std::atoi(e) != 0;
+	if (const char *e = std::getenv("PRT_B200_REFILL"))
+		c->refill = std::max(0, std::min(32, std::atoi(e)));
 	c->name = prop.name;
 	*out = c;
 	return PRT_OK;
@@ -153,8 +158,20 @@ static int timed_build(prt_b200 *c, const float *d_tris9, uint64_t n, float *ms)
 	if (rc)
 		return rc;
 	PRT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+	// scene bounds for the fast box test's error margin: the root node carries both halves
+	prt::Node root;
+	if (c->n_nodes)
+		PRT_CUDA(c, cudaMemcpyAsync(&root, c->nodes.p, sizeof root, cudaMemcpyDeviceToHost, c->stream));
 	PRT_CUDA(c, cudaStreamSynchronize(c->stream));
 	PRT_CUDA(c, cudaEventElapsedTime(&c->last_build_ms, c->ev0, c->ev1));
+	for (int a = 0; a < 3; ++a) {
+		float m = 0.f;
+		if (c->n_nodes) {
+			m = std::max(std::fabs(root.lo0[a]), std::fabs(root.hi0[a]));
+			m = std::max(m, std::max(std::fabs(root.lo1[a]), std::fabs(root.hi1[a])));
+		}
+		c->scene_absmax[a] = m;
+	}
 	if (ms)
 		*ms = c->last_build_ms;
 	return PRT_OK;
@@ -315,6 +332,27 @@ int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t 
 	}
 	PRT_CUDA(c, cudaStreamSynchronize(c->stream));
 	PRT_CUDA(c, cudaEventElapsedTime(&c->last_trace_ms, c->ev0, c->ev1));
+	return PRT_OK;
+}
+
+// Bandwidth probe: a persistent grid repeatedly reads `bytes` of device memory with 16-byte
+// loads.  With bytes << L2 (126 MB) it measures L2 read bandwidth, with bytes >> L2 HBM read
+// bandwidth -- the denominators of the traversal roofline, measured on this box.
+int prt_b200_read_bandwidth(prt_b200 *c, uint64_t bytes, int iters, float *gbs) {
+	if (!c || !gbs || bytes < 4096 || iters < 1)
+		return fail(c, PRT_E_ARG, "read_bandwidth: bad argument");
+	PRT_CUDA(c, cudaSetDevice(c->device));
+	void *buf = nullptr;
+	PRT_CUDA(c, cudaMalloc(&buf, bytes));
+	cudaMemsetAsync(buf, 1, bytes, c->stream);
+	float ms = 0.f;
+	int rc = prt::launch_read_probe(c, buf, bytes, 1, nullptr); // warm
+	if (!rc)
+		rc = prt::launch_read_probe(c, buf, bytes, iters, &ms);
+	cudaFree(buf);
+	if (rc)
+		return rc;
+	*gbs = (float)((double)bytes * iters / (ms * 1e-3) / 1e9);
 	return PRT_OK;
 }
 

@@ -7,7 +7,7 @@
 //   3 sort      LSD radix sort, 8-bit digits, (u64 key, u32 index), tiles ranked in shared memory
 //               with warp-level match/prefix ranking, coalesced scatter
 //   4 karras    one thread per internal node: range + split (Karras 2012), parent links
-//   5 leaves    gather triangles into Morton order as 48-byte records + exact leaf AABBs
+//   5 leaves    gather triangles into Morton order as 64-byte records (v0, edges, own AABB)
 //   6 refit     bottom-up, second-arriver-continues with one atomic counter per node; writes the
 //               final 64-byte nodes that carry both children's exact boxes
 // HBM-bound integer/byte work: no tensor cores.  Algorithmic bytes per triangle are tallied in
@@ -377,8 +377,9 @@ __global__ void __launch_bounds__(256)
 	float4 *rec = reinterpret_cast<float4 *>(recs + j);
 	// edges exactly as core.hpp:33-35 computes them
 	rec[0] = make_float4(t[0], t[1], t[2], __uint_as_float(prim));
-	rec[1] = make_float4(fsub(t[3], t[0]), fsub(t[4], t[1]), fsub(t[5], t[2]), 0.0f);
-	rec[2] = make_float4(fsub(t[6], t[0]), fsub(t[7], t[1]), fsub(t[8], t[2]), 0.0f);
+	rec[1] = make_float4(fsub(t[3], t[0]), fsub(t[4], t[1]), fsub(t[5], t[2]), b.lo[0]);
+	rec[2] = make_float4(fsub(t[6], t[0]), fsub(t[7], t[1]), fsub(t[8], t[2]), b.lo[1]);
+	rec[3] = make_float4(b.lo[2], b.hi[0], b.hi[1], b.hi[2]);
 	leaf_box[2 * j] = make_float4(b.lo[0], b.lo[1], b.lo[2], 0.0f);
 	leaf_box[2 * j + 1] = make_float4(b.hi[0], b.hi[1], b.hi[2], 0.0f);
 }
@@ -433,24 +434,26 @@ __global__ void __launch_bounds__(256)
 	}
 }
 
-// single-triangle scene (bvh.hpp:165-181): one root whose first child is the triangle
-__global__ void k_single(Node *nodes, const float4 *leaf_box) {
+// single-triangle scene (bvh.hpp:165-181): a root whose first child is the triangle and whose
+// second child is a zero-area dummy record (det == 0 in intersect_tri, so it can never be hit)
+__global__ void k_single(Node *nodes, TriRec *recs, const float4 *leaf_box) {
 	Node nd;
 	const float4 lo = leaf_box[0], hi = leaf_box[1];
-	nd.lo0[0] = lo.x;
-	nd.lo0[1] = lo.y;
-	nd.lo0[2] = lo.z;
-	nd.hi0[0] = hi.x;
-	nd.hi0[1] = hi.y;
-	nd.hi0[2] = hi.z;
-	for (int a = 0; a < 3; ++a) {
-		nd.lo1[a] = INFINITY;
-		nd.hi1[a] = -INFINITY;
-	}
+	nd.lo0[0] = nd.lo1[0] = lo.x;
+	nd.lo0[1] = nd.lo1[1] = lo.y;
+	nd.lo0[2] = nd.lo1[2] = lo.z;
+	nd.hi0[0] = nd.hi1[0] = hi.x;
+	nd.hi0[1] = nd.hi1[1] = hi.y;
+	nd.hi0[2] = nd.hi1[2] = hi.z;
 	nd.child0 = ~0;
-	nd.child1 = PRT_NO_CHILD;
+	nd.child1 = ~1;
 	nd.pad0 = nd.pad1 = 0;
 	nodes[0] = nd;
+	float4 *rec = reinterpret_cast<float4 *>(recs + 1);
+	rec[0] = make_float4(lo.x, lo.y, lo.z, __uint_as_float(0xffffffffu));
+	rec[1] = make_float4(0.f, 0.f, 0.f, lo.x);
+	rec[2] = make_float4(0.f, 0.f, 0.f, lo.y);
+	rec[3] = make_float4(lo.z, hi.x, hi.y, hi.z);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -475,7 +478,7 @@ int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 
 	const uint32_t n_tiles = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
 	PRT_CUDA(c, c->nodes.reserve(c->n_nodes * sizeof(Node)));
-	PRT_CUDA(c, c->trirecs.reserve(n * sizeof(TriRec)));
+	PRT_CUDA(c, c->trirecs.reserve((n + 1) * sizeof(TriRec)));
 	PRT_CUDA(c, c->keys[0].reserve(n * 8));
 	PRT_CUDA(c, c->keys[1].reserve(n * 8));
 	PRT_CUDA(c, c->vals[0].reserve(n * 4));
@@ -521,7 +524,7 @@ int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 	                           c->leaf_box.as<float4>());
 	c->launches += 1;
 	if (n == 1) {
-		k_single<<<1, 1, 0, s>>>(c->nodes.as<Node>(), c->leaf_box.as<float4>());
+		k_single<<<1, 1, 0, s>>>(c->nodes.as<Node>(), c->trirecs.as<TriRec>(), c->leaf_box.as<float4>());
 		c->launches += 1;
 	} else {
 		PRT_CUDA(c, cudaMemsetAsync(c->flags.p, 0, (n - 1) * 4, s));

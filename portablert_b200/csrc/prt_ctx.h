@@ -92,6 +92,9 @@ struct prt_b200 {
 
 	prt_trace_opts opts{1, 1e-4f, 64.0f};
 
+	float scene_absmax[3] = {0.f, 0.f, 0.f}; // largest |coordinate| per axis (fast box-test margin)
+	int fast_boxes = 1;                      // env PRT_B200_FAST_BOXES=0 forces the exact test everywhere
+	int refill = 24;                         // env PRT_B200_REFILL: dynamic ray-fetch threshold (lanes)
 	uint64_t launches = 0;
 	float last_build_ms = 0.f, last_trace_ms = 0.f;
 };
@@ -128,5 +131,7 @@ struct TraceOut {
 };
 int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, const TraceOut &out,
                  uint32_t *d_counts, cudaStream_t stream);
+
+int launch_read_probe(prt_b200 *c, const void *buf, uint64_t bytes, int iters, float *ms);
 
 } // namespace prt

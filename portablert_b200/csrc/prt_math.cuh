@@ -46,7 +46,8 @@ PRT_HD float smax(float a, float b) { return (a < b) ? b : a; }
 // ray_box_intersect) is done by its parent without touching the triangle.
 //   child < 0            : leaf, triangle record index = ~child
 //   child >= 0           : internal node index
-//   child == PRT_NO_CHILD: absent (single-triangle scene, bvh.hpp:165-181)
+// A single-triangle scene (bvh.hpp:165-181) gets a root whose second child is a zero-area dummy
+// triangle record, so the traversal loop needs no "absent child" case.
 struct __attribute__((aligned(16))) Node {
 	float lo0[3];
 	float hi0[3];
@@ -59,18 +60,20 @@ static_assert(sizeof(Node) == 64, "Node must be 64 bytes");
 
 #define PRT_NO_CHILD ((int32_t)0x7fffffff)
 
-// Triangle record (48 B, three 16-byte loads), stored in Morton order: v0 and the two edges
-// exactly as intersect_tri computes them (core.hpp:33-35: edge = v1 - v0, v2 - v0 in binary32), plus
-// the caller's triangle index (= primitive_id).
+// Triangle record (64 B, four 16-byte loads), stored in Morton order: v0 and the two edges exactly as
+// intersect_tri computes them (core.hpp:33-35: edge = v1 - v0, v2 - v0 in binary32), the caller's
+// triangle index (= primitive_id) and the triangle's own AABB exactly as make_aabb computes it
+// (bvh.hpp:28-37) -- the box the reference tests right before intersect_tri (bvh.hpp:237-246).
 struct __attribute__((aligned(16))) TriRec {
 	float v0[3];
 	uint32_t prim;
 	float e1[3];
-	uint32_t pad1;
+	float lox;
 	float e2[3];
-	uint32_t pad2;
+	float loy;
+	float loz, hix, hiy, hiz;
 };
-static_assert(sizeof(TriRec) == 48, "TriRec must be 48 bytes");
+static_assert(sizeof(TriRec) == 64, "TriRec must be 64 bytes");
 
 struct Box {
 	float lo[3], hi[3];

@@ -47,113 +47,225 @@ inline float u2f(uint32_t u) {
 }
 #endif
 
+#if defined(__CUDA_ARCH__)
+#define PRT_WARP_ANY(x) __any_sync(__activemask(), (x))
+#else
+#define PRT_WARP_ANY(x) (x)
+#endif
+
 struct StackEntry {
 	uint32_t node;
 	uint32_t tmin_bits;
 };
 
-// Nearest hit of one ray.  Reproduces the result of BVH2::nearest_tri (bvh.hpp:224-265) over a
-// different tree: box tests and the triangle test are the reference's own arithmetic
-// (prt_math.cuh), entry order and pruning only change how many boxes are looked at.
-template <bool ANYHIT, bool WANT_UV, bool TRACK_PRIM, bool COUNT>
-PRT_HD void traverse(const Node *nodes, const TriRec *tris, uint64_t n_tris_scene, const RayC &r,
-                     const TraverseOpts &opt, Hit &out) {
-	float t_best = INFINITY, u_best = 0.0f, v_best = 0.0f;
-	uint32_t prim_best = 0xffffffffu;
-	float limit = INFINITY;
+// ---------------------------------------------------------------------------------------------
+// Conservative fast box test for INTERNAL culling.
+//
+// The reference slab arithmetic RN(RN(b - o) * idir) costs 2 ops per plane plus NaN-faithful
+// min/max (2 ops each).  Whether an internal box is entered does not have to replay that: it only
+// has to be CONSERVATIVE with respect to it (never reject a box the reference arithmetic would
+// pass).  The fast test uses one FFMA per plane, t' = fma(b, idir, -RN(o*idir)), plain FMNMX
+// min/max, and widens the interval by a margin M that bounds |t' - t_ref|:
+//     t_ref = T(1+e1)(1+e2),  t' = (T - o*idir*e3)(1+e4),  T = (b-o)*idir exact, |e| <= 2^-24
+//     => |t' - t_ref| <= 2^-24 (|o*idir| + 3.01 |T|) <= 2^-22 (|o_a| + B_a) |idir_a|
+// with B_a the largest |coordinate| of the scene on axis a.  M is taken as TWICE that bound,
+// maximised over the axes, which also covers the rounding of the margin arithmetic itself.
+// A child that is a LEAF (its box is the triangle's own AABB, i.e. the reference's per-leaf
+// ray_box_intersect) is re-tested with the exact reference arithmetic before the triangle is
+// touched, so the fast test never decides a result -- it only skips subtrees.
+// Rays with a zero / denormal / very small direction component (|d_a| < 2^-12 max|d|), or
+// non-finite intermediates, do not qualify and take the exact path for every box.
+struct FastRay {
+	float idir[3], c[3]; // t' = fma(b, idir, c), c = -RN(o * idir)
+	float M;             // margin (see above)
+	bool ok;
+};
+
+PRT_HD FastRay make_fast_ray(const RayC &r, const float *scene_absmax) {
+	FastRay f;
+	float M = 0.0f;
+	const float dmax = fmaxf(fmaxf(fabsf(r.d[0]), fabsf(r.d[1])), fabsf(r.d[2]));
+	bool ok = dmax < INFINITY;
+#pragma unroll
+	for (int a = 0; a < 3; ++a) {
+		f.idir[a] = r.idir[a];
+		const float oi = fmul(r.o[a], r.idir[a]);
+		f.c[a] = -oi;
+		const float m = fmul(fmul(4.76837158e-7f /* 2^-21 */, fadd(fabsf(r.o[a]), scene_absmax[a])),
+		                     fabsf(r.idir[a]));
+		M = fmaxf(M, m);
+		ok = ok && (fabsf(r.d[a]) >= fmul(dmax, 2.44140625e-4f /* 2^-12 */)) &&
+		     (fabsf(oi) < 1.0e30f) && (fabsf(r.idir[a]) < 1.0e30f);
+	}
+	f.M = M;
+	f.ok = ok && (M < 1.0e30f) && (M == M);
+	return f;
+}
+
+// returns conservative pass; tmin_out is a lower bound (minus nothing: compare against limit + M)
+PRT_HD bool slab_fast(const FastRay &f, const float *lo, const float *hi, float &tmin_out) {
+#if defined(__CUDA_ARCH__)
+#define PRT_FMA(a, b, c) __fmaf_rn(a, b, c)
+#else
+#define PRT_FMA(a, b, c) fmaf(a, b, c)
+#endif
+	const float x0 = PRT_FMA(lo[0], f.idir[0], f.c[0]), x1 = PRT_FMA(hi[0], f.idir[0], f.c[0]);
+	const float y0 = PRT_FMA(lo[1], f.idir[1], f.c[1]), y1 = PRT_FMA(hi[1], f.idir[1], f.c[1]);
+	const float z0 = PRT_FMA(lo[2], f.idir[2], f.c[2]), z1 = PRT_FMA(hi[2], f.idir[2], f.c[2]);
+#undef PRT_FMA
+	const float tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
+	const float tmax = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+	tmin_out = tmin;
+	// reference: reject iff tmax < 0 or tmin > tmax; widened by M on both ends
+	return (tmax >= -f.M) && (fsub(tmin, tmax) <= fadd(f.M, f.M));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-ray traversal state machine.  One call of trav_step() handles one tree element:
+//   internal node : both children's boxes are tested (fast conservative test, or the reference's
+//                   arithmetic when the ray does not qualify), the nearer passing child is entered,
+//                   the other is pushed with its entry distance
+//   leaf          : the triangle's own AABB is tested with the reference's ray_box_intersect, then
+//                   intersect_tri; the best hit and the pruning limits are updated
+// followed by a pop that discards stacked subtrees whose entry distance exceeds the best hit
+// (+ slack).  The result is the minimum over all accepted triangles under an order-independent tie
+// rule, so neither the visit order nor the pruning can change it.
+struct TravState {
+	float t_best, u_best, v_best;
+	uint32_t prim_best;
+	float limit;  // exact entry distances are compared against this
+	float limitM; // fast (lower-bound) entry distances against limit + M
+	float slack_abs;
+	int sp;
+	int32_t cur; // >= 0 internal node, < 0 leaf (~index), PRT_DONE finished
+	uint32_t n_nodes, n_tris;
+};
+
+#define PRT_DONE ((int32_t)0x7fffffff)
+
+PRT_HD void trav_init(TravState &s, const RayC &r, const TraverseOpts &opt, uint64_t n_tris_scene) {
+	s.t_best = INFINITY;
+	s.u_best = 0.0f;
+	s.v_best = 0.0f;
+	s.prim_best = 0xffffffffu;
+	s.limit = INFINITY;
+	s.limitM = INFINITY;
 	// absolute part of the pruning slack: a few ulps of the origin's magnitude expressed in
 	// ray-parameter units (NaN/inf here simply disables pruning for this ray)
 	const float omax = fmaxf(fmaxf(fabsf(r.o[0]), fabsf(r.o[1])), fabsf(r.o[2]));
 	const float dmax = fmaxf(fmaxf(fabsf(r.d[0]), fabsf(r.d[1])), fabsf(r.d[2]));
-	const float slack_abs = fmul(fmul(opt.slack_ulps, 1.1920929e-7f), fdiv(omax, dmax));
-	uint32_t n_nodes = 0, n_tris = 0;
+	s.slack_abs = fmul(fmul(opt.slack_ulps, 1.1920929e-7f), fdiv(omax, dmax));
+	s.sp = 0;
+	s.cur = n_tris_scene == 0 ? PRT_DONE : 0;
+	s.n_nodes = 0;
+	s.n_tris = 0;
+}
 
-	StackEntry stack[STACK_DEPTH];
-	int sp = 0;
-	int32_t cur = 0;
-	bool done = n_tris_scene == 0;
-	while (!done) {
-		bool pop = true;
-		if (cur >= 0) {
-			const char *np = reinterpret_cast<const char *>(nodes + cur);
-			const Vec4 a = ld16(np), b = ld16(np + 16), c = ld16(np + 32), d = ld16(np + 48);
-			const int32_t c0 = (int32_t)f2u(d.x), c1 = (int32_t)f2u(d.y);
-			if (COUNT)
-				++n_nodes;
-			const float lo0[3] = {a.x, a.y, a.z}, hi0[3] = {a.w, b.x, b.y};
-			const float lo1[3] = {b.z, b.w, c.x}, hi1[3] = {c.y, c.z, c.w};
-			float tm0, tm1;
-			bool h0 = slab_ref(r, lo0, hi0, tm0);
-			bool h1 = slab_ref(r, lo1, hi1, tm1);
-			h1 = h1 && (c1 != PRT_NO_CHILD);
-			if (opt.prune) {
-				h0 = h0 && !(tm0 > limit);
-				h1 = h1 && !(tm1 > limit);
-			}
-			if (h0 && h1) {
-				const bool first0 = !(tm1 < tm0);
-				stack[sp].node = (uint32_t)(first0 ? c1 : c0);
-				stack[sp].tmin_bits = f2u(first0 ? tm1 : tm0);
-				++sp;
-				cur = first0 ? c0 : c1;
-				pop = false;
-			} else if (h0 || h1) {
-				cur = h0 ? c0 : c1;
-				pop = false;
-			}
+template <bool ANYHIT, bool WANT_UV, bool TRACK_PRIM, bool COUNT, bool FAST>
+PRT_HD void trav_step(TravState &s, StackEntry *stack, const Node *nodes, const TriRec *tris,
+                      const RayC &r, const FastRay &fr, const TraverseOpts &opt) {
+	bool pop = true;
+	if (s.cur >= 0) {
+		const char *np = reinterpret_cast<const char *>(nodes + s.cur);
+		const Vec4 a = ld16(np), b = ld16(np + 16), c = ld16(np + 32), d = ld16(np + 48);
+		const int32_t c0 = (int32_t)f2u(d.x), c1 = (int32_t)f2u(d.y);
+		if (COUNT)
+			++s.n_nodes;
+		const float lo0[3] = {a.x, a.y, a.z}, hi0[3] = {a.w, b.x, b.y};
+		const float lo1[3] = {b.z, b.w, c.x}, hi1[3] = {c.y, c.z, c.w};
+		float tm0, tm1;
+		bool h0, h1;
+		if (FAST) {
+			h0 = slab_fast(fr, lo0, hi0, tm0) && !(tm0 > s.limitM);
+			h1 = slab_fast(fr, lo1, hi1, tm1) && !(tm1 > s.limitM);
 		} else {
-			const char *tp = reinterpret_cast<const char *>(tris + (uint32_t)(~cur));
-			const Vec4 q0 = ld16(tp), q1 = ld16(tp + 16), q2 = ld16(tp + 32);
-			if (COUNT)
-				++n_tris;
-			const float v0[3] = {q0.x, q0.y, q0.z};
-			const float e1[3] = {q1.x, q1.y, q1.z};
-			const float e2[3] = {q2.x, q2.y, q2.z};
-			const uint32_t prim = f2u(q0.w);
-			float t, u, v;
-			if (moller_trumbore_ref(r, v0, e1, e2, t, u, v)) {
+			h0 = slab_ref(r, lo0, hi0, tm0) && !(tm0 > s.limit);
+			h1 = slab_ref(r, lo1, hi1, tm1) && !(tm1 > s.limit);
+		}
+		if (h0 && h1) {
+			const bool first0 = !(tm1 < tm0);
+			stack[s.sp].node = (uint32_t)(first0 ? c1 : c0);
+			stack[s.sp].tmin_bits = f2u(first0 ? tm1 : tm0);
+			++s.sp;
+			s.cur = first0 ? c0 : c1;
+			pop = false;
+		} else if (h0 || h1) {
+			s.cur = h0 ? c0 : c1;
+			pop = false;
+		}
+	} else {
+		const char *tp = reinterpret_cast<const char *>(tris + (uint32_t)(~s.cur));
+		const Vec4 q0 = ld16(tp), q1 = ld16(tp + 16), q2 = ld16(tp + 32), q3 = ld16(tp + 48);
+		if (COUNT)
+			++s.n_tris;
+		// Both of the reference's tests must pass (ray_box_intersect on the triangle's own AABB,
+		// bvh.hpp:237, then intersect_tri, bvh.hpp:246); they are pure functions, so the cheaper
+		// rejecter runs first: Moeller-Trumbore, then the exact box verdict only for accepted hits.
+		// On the exact path the parent already applied that verdict to this very box.
+		const float v0[3] = {q0.x, q0.y, q0.z};
+		const float e1[3] = {q1.x, q1.y, q1.z};
+		const float e2[3] = {q2.x, q2.y, q2.z};
+		const uint32_t prim = f2u(q0.w);
+		float t, u, v;
+		if (moller_trumbore_ref(r, v0, e1, e2, t, u, v)) {
+			const bool better = ANYHIT ? (t < s.t_best)
+			                           : (TRACK_PRIM ? closer(t, prim, s.t_best, s.prim_best)
+			                                         : (t < s.t_best));
+			bool box_ok = true;
+			if (FAST && better) {
+				const float lo[3] = {q1.w, q2.w, q3.x}, hi[3] = {q3.y, q3.z, q3.w};
+				float tm;
+				box_ok = slab_ref(r, lo, hi, tm);
+			}
+			if (better && box_ok) {
 				if (ANYHIT) {
 					// `valid` is t_near < inf (bvh.hpp:260): any candidate with t < inf decides it
 					// (a NaN or +inf t never updates t_near, bvh.hpp:247)
-					if (t < t_best) {
-						t_best = t;
-						break;
-					}
-				} else {
-					const bool better =
-					    TRACK_PRIM ? closer(t, prim, t_best, prim_best) : (t < t_best);
-					if (better) {
-						t_best = t;
-						prim_best = prim;
-						if (WANT_UV) {
-							u_best = u;
-							v_best = v;
-						}
-						limit = fadd(t_best, fadd(fmul(fabsf(t_best), opt.slack_rel), slack_abs));
-					}
+					s.t_best = t;
+					s.cur = PRT_DONE;
+					return;
+				}
+				s.t_best = t;
+				s.prim_best = prim;
+				if (WANT_UV) {
+					s.u_best = u;
+					s.v_best = v;
+				}
+				if (opt.prune) {
+					s.limit = fadd(t, fadd(fmul(fabsf(t), opt.slack_rel), s.slack_abs));
+					s.limitM = FAST ? fadd(s.limit, fr.M) : s.limit;
 				}
 			}
 		}
-		if (pop) {
-			for (;;) {
-				if (sp == 0) {
-					done = true;
-					break;
-				}
-				--sp;
-				if (opt.prune && u2f(stack[sp].tmin_bits) > limit)
-					continue;
-				cur = (int32_t)stack[sp].node;
+	}
+	if (pop) {
+		s.cur = PRT_DONE;
+		while (s.sp > 0) {
+			--s.sp;
+			// a stacked entry distance is a lower bound within M on the fast path
+			if (!(u2f(stack[s.sp].tmin_bits) > (FAST ? s.limitM : s.limit))) {
+				s.cur = (int32_t)stack[s.sp].node;
 				break;
 			}
 		}
 	}
-	out.t = t_best;
-	out.u = u_best;
-	out.v = v_best;
-	out.prim = prim_best;
-	out.n_nodes = n_nodes;
-	out.n_tris = n_tris;
+}
+
+// Scalar driver (instrumented kernel and the host-side emulator): one ray start to finish.
+template <bool ANYHIT, bool WANT_UV, bool TRACK_PRIM, bool COUNT, bool FAST>
+PRT_HD void traverse(const Node *nodes, const TriRec *tris, uint64_t n_tris_scene, const RayC &r,
+                     const FastRay &fr, const TraverseOpts &opt, Hit &out) {
+	TravState s;
+	StackEntry stack[STACK_DEPTH];
+	trav_init(s, r, opt, n_tris_scene);
+	while (s.cur != PRT_DONE)
+		trav_step<ANYHIT, WANT_UV, TRACK_PRIM, COUNT, FAST>(s, stack, nodes, tris, r, fr, opt);
+	out.t = s.t_best;
+	out.u = s.u_best;
+	out.v = s.v_best;
+	out.prim = s.prim_best;
+	out.n_nodes = s.n_nodes;
+	out.n_tris = s.n_tris;
 }
 
 } // namespace prt

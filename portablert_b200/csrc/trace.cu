@@ -38,7 +38,61 @@ struct TraceParams {
 	unsigned long long *counter;
 	int prune;
 	float slack_rel, slack_ulps;
+	float scene_absmax[3];
+	int fast; // 1: conservative FFMA test for internal culling where the ray qualifies
+	int refill; // re-fetch rays when fewer than this many lanes of a warp are still traversing
 };
+
+// Writes one finished ray (epilogue of bvh.hpp:259-263).
+template <uint32_t MASK, bool AOS, bool COUNT>
+__device__ __forceinline__ void write_hit(const TraceParams &P, uint64_t i, const RayC &r,
+                                          const TravState &s) {
+	const bool valid = s.t_best < INFINITY;
+	const float px = fadd(r.o[0], fmul(s.t_best, r.d[0]));
+	const float py = fadd(r.o[1], fmul(s.t_best, r.d[1]));
+	const float pz = fadd(r.o[2], fmul(s.t_best, r.d[2]));
+	if (COUNT) {
+		P.counts[2 * i] = s.n_nodes;
+		P.counts[2 * i + 1] = s.n_tris;
+	} else if (AOS) {
+		char *rec = P.aos + i * P.lay.stride;
+		if (MASK & PRT_TAG_UV) {
+			*reinterpret_cast<float *>(rec + P.lay.off_u) = s.u_best;
+			*reinterpret_cast<float *>(rec + P.lay.off_v) = s.v_best;
+		}
+		if (MASK & PRT_TAG_T)
+			*reinterpret_cast<float *>(rec + P.lay.off_t) = s.t_best;
+		if (MASK & PRT_TAG_PID)
+			*reinterpret_cast<uint32_t *>(rec + P.lay.off_pid) = s.prim_best;
+		if (MASK & PRT_TAG_VALID)
+			*reinterpret_cast<uint8_t *>(rec + P.lay.off_valid) = valid ? 1 : 0;
+		if (MASK & PRT_TAG_P) {
+			*reinterpret_cast<float *>(rec + P.lay.off_px) = px;
+			*reinterpret_cast<float *>(rec + P.lay.off_py) = py;
+			*reinterpret_cast<float *>(rec + P.lay.off_pz) = pz;
+		}
+	} else {
+		if (MASK & PRT_TAG_UV)
+			P.uv[i] = make_float2(s.u_best, s.v_best);
+		if (MASK & PRT_TAG_T)
+			P.t[i] = s.t_best;
+		if (MASK & PRT_TAG_PID)
+			P.pid[i] = s.prim_best;
+		if (MASK & PRT_TAG_VALID)
+			P.valid[i] = valid ? 1 : 0;
+		if (MASK & PRT_TAG_P) {
+			P.p[3 * i] = px;
+			P.p[3 * i + 1] = py;
+			P.p[3 * i + 2] = pz;
+		}
+	}
+}
+
+// Persistent warps with dynamic ray fetch: a lane whose ray has finished writes its hit and, as
+// soon as fewer than REFILL lanes of the warp are still traversing, all idle lanes pull new rays
+// from the global counter with one aggregated atomic.  Rays of very different length (a miss ends
+// after a node or two, a hit after dozens) therefore do not leave most of the warp idle.
+// (threshold P.refill, env PRT_B200_REFILL; 0 = classic "whole warp finishes, then fetch 32")
 
 template <uint32_t MASK, bool AOS, bool COUNT>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceParams P) {
@@ -46,68 +100,69 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceParams P) {
 	constexpr bool WANT_UV = (MASK & PRT_TAG_UV) != 0;
 	constexpr bool TRACK_PRIM = (MASK & (PRT_TAG_UV | PRT_TAG_PID)) != 0;
 
-	const int lane = threadIdx.x & 31;
+	const unsigned lane = threadIdx.x & 31;
+	const unsigned lt = (1u << lane) - 1u;
 	TraverseOpts opts;
 	opts.prune = P.prune;
 	opts.slack_rel = P.slack_rel;
 	opts.slack_ulps = P.slack_ulps;
 
-	for (;;) {
-		unsigned long long base = 0;
-		if (lane == 0)
-			base = atomicAdd(P.counter, 32ull);
-		base = __shfl_sync(0xffffffffu, base, 0);
-		if (base >= P.n_rays)
-			break;
-		const uint64_t i = base + lane;
-		if (i < P.n_rays) {
-			float r6[6];
-#pragma unroll
-			for (int k = 0; k < 6; ++k)
-				r6[k] = __ldg(P.rays + i * 6 + k);
-			const RayC r = make_ray(r6);
-			Hit h;
-			traverse<ANYHIT, WANT_UV, TRACK_PRIM, COUNT>(P.nodes, P.tris, P.n_tris, r, opts, h);
+	StackEntry stack[STACK_DEPTH];
+	TravState s;
+	RayC r;
+	FastRay fr;
+	uint64_t ray = 0;
+	bool has_ray = false;
+	bool fast = false;
+	bool exhausted = false; // warp-uniform: the global counter ran past the last ray
+	s.cur = PRT_DONE;
 
-			// epilogue, bvh.hpp:259-263
-			const bool valid = h.t < INFINITY;
-			const float px = fadd(r.o[0], fmul(h.t, r.d[0]));
-			const float py = fadd(r.o[1], fmul(h.t, r.d[1]));
-			const float pz = fadd(r.o[2], fmul(h.t, r.d[2]));
-			if (COUNT) {
-				P.counts[2 * i] = h.n_nodes;
-				P.counts[2 * i + 1] = h.n_tris;
-			} else if (AOS) {
-				char *rec = P.aos + i * P.lay.stride;
-				if (MASK & PRT_TAG_UV) {
-					*reinterpret_cast<float *>(rec + P.lay.off_u) = h.u;
-					*reinterpret_cast<float *>(rec + P.lay.off_v) = h.v;
+	for (;;) {
+		// ---- fetch rays for the idle lanes (one atomic per warp)
+		const unsigned idle = __ballot_sync(0xffffffffu, !has_ray);
+		if (idle && !exhausted) {
+			const int n = __popc(idle);
+			const int leader = __ffs(idle) - 1;
+			unsigned long long base = 0;
+			if ((int)lane == leader)
+				base = atomicAdd(P.counter, (unsigned long long)n);
+			base = __shfl_sync(0xffffffffu, base, leader);
+			if (base + n >= P.n_rays)
+				exhausted = true;
+			if (!has_ray) {
+				const uint64_t i = base + __popc(idle & lt);
+				if (i < P.n_rays) {
+					float r6[6];
+#pragma unroll
+					for (int k = 0; k < 6; ++k)
+						r6[k] = __ldg(P.rays + i * 6 + k);
+					r = make_ray(r6);
+					fr = make_fast_ray(r, P.scene_absmax);
+					fast = P.fast && fr.ok;
+					trav_init(s, r, opts, P.n_tris);
+					ray = i;
+					has_ray = true;
 				}
-				if (MASK & PRT_TAG_T)
-					*reinterpret_cast<float *>(rec + P.lay.off_t) = h.t;
-				if (MASK & PRT_TAG_PID)
-					*reinterpret_cast<uint32_t *>(rec + P.lay.off_pid) = h.prim;
-				if (MASK & PRT_TAG_VALID)
-					*reinterpret_cast<uint8_t *>(rec + P.lay.off_valid) = valid ? 1 : 0;
-				if (MASK & PRT_TAG_P) {
-					*reinterpret_cast<float *>(rec + P.lay.off_px) = px;
-					*reinterpret_cast<float *>(rec + P.lay.off_py) = py;
-					*reinterpret_cast<float *>(rec + P.lay.off_pz) = pz;
-				}
-			} else {
-				if (MASK & PRT_TAG_UV)
-					P.uv[i] = make_float2(h.u, h.v);
-				if (MASK & PRT_TAG_T)
-					P.t[i] = h.t;
-				if (MASK & PRT_TAG_PID)
-					P.pid[i] = h.prim;
-				if (MASK & PRT_TAG_VALID)
-					P.valid[i] = valid ? 1 : 0;
-				if (MASK & PRT_TAG_P) {
-					P.p[3 * i] = px;
-					P.p[3 * i + 1] = py;
-					P.p[3 * i + 2] = pz;
-				}
+			}
+		}
+		if (!__any_sync(0xffffffffu, has_ray))
+			break;
+
+		// ---- traverse until this lane's ray is finished or too few lanes are still busy
+		if (has_ray) {
+			while (s.cur != PRT_DONE) {
+				if (fast)
+					trav_step<ANYHIT, WANT_UV, TRACK_PRIM, COUNT, true>(s, stack, P.nodes, P.tris, r,
+					                                                    fr, opts);
+				else
+					trav_step<ANYHIT, WANT_UV, TRACK_PRIM, COUNT, false>(s, stack, P.nodes, P.tris, r,
+					                                                     fr, opts);
+				if (!exhausted && __popc(__activemask()) < P.refill)
+					break;
+			}
+			if (s.cur == PRT_DONE) {
+				write_hit<MASK, AOS, COUNT>(P, ray, r, s);
+				has_ray = false;
 			}
 		}
 		__syncwarp();
@@ -161,6 +216,10 @@ int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, c
 	P.prune = c->opts.prune;
 	P.slack_rel = c->opts.slack_rel;
 	P.slack_ulps = c->opts.slack_ulps;
+	for (int a = 0; a < 3; ++a)
+		P.scene_absmax[a] = c->scene_absmax[a];
+	P.fast = c->fast_boxes;
+	P.refill = c->refill;
 	PRT_CUDA(c, c->counter.reserve(256));
 	P.counter = c->counter.as<unsigned long long>();
 	PRT_CUDA(c, cudaMemsetAsync(P.counter, 0, 8, s));
@@ -182,6 +241,37 @@ int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, c
 	fn<<<(unsigned)grid, TRACE_THREADS, 0, s>>>(P);
 	c->launches += 1;
 	PRT_CUDA(c, cudaGetLastError());
+	return PRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// read-bandwidth probe (roofline denominators)
+__global__ void __launch_bounds__(256) k_read_probe(const uint4 *__restrict__ p, uint64_t n16,
+                                                    int iters, uint32_t *sink) {
+	uint32_t acc = 0;
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (int it = 0; it < iters; ++it) {
+		for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+			const uint4 v = __ldcg(p + i); // L2 (not L1) path
+			acc += v.x ^ v.y ^ v.z ^ v.w;
+		}
+	}
+	if (acc == 0x12345678u)
+		*sink = acc; // never true in practice; keeps the loads alive
+}
+
+int launch_read_probe(prt_b200 *c, const void *buf, uint64_t bytes, int iters, float *ms) {
+	PRT_CUDA(c, c->counter.reserve(256));
+	PRT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+	k_read_probe<<<c->sm_count * 8, 256, 0, c->stream>>>(static_cast<const uint4 *>(buf), bytes / 16,
+	                                                     iters, c->counter.as<uint32_t>() + 8);
+	c->launches += 1;
+	PRT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+	PRT_CUDA(c, cudaStreamSynchronize(c->stream));
+	float t = 0.f;
+	PRT_CUDA(c, cudaEventElapsedTime(&t, c->ev0, c->ev1));
+	if (ms)
+		*ms = t;
 	return PRT_OK;
 }
 

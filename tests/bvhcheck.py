@@ -1,4 +1,4 @@
-"""Structural checks of a built BVH (nodes (n,16) float32 view of 64-byte nodes, tris (n,12))."""
+"""Structural checks of a built BVH (nodes (n,16) float32 view of 64-byte nodes, tris (n,16): the 64-byte triangle records)."""
 import numpy as np
 
 NO_CHILD = 0x7FFFFFFF
@@ -21,6 +21,8 @@ def check_bvh(nodes, trirecs, tris):
     assert np.array_equal(trirecs[:, 8:11], src[:, 6:9] - src[:, 0:3])
     v = src.reshape(n, 3, 3)
     leaf_lo, leaf_hi = v.min(1), v.max(1)
+    # the record carries the triangle's own AABB (make_aabb, bvh.hpp:28-37)
+    assert np.array_equal(trirecs[:, [7, 11, 12]], leaf_lo) and np.array_equal(trirecs[:, 13:16], leaf_hi)
 
     ch = nodes[:, 12:14].copy().view(np.int32)
     box = nodes[:, :12]
@@ -41,16 +43,17 @@ def check_bvh(nodes, trirecs, tris):
             seen_node[node] = True
             stack.append((node, 1, d))
             for c in ch[node]:
-                if c >= 0 and c != NO_CHILD:
+                if c >= 0:
                     stack.append((int(c), 0, d + 1))
         else:
             for k, c in enumerate(ch[node]):
                 blo = box[node, 6 * k:6 * k + 3]
                 bhi = box[node, 6 * k + 3:6 * k + 6]
-                if c == NO_CHILD:
-                    continue
                 if c < 0:
                     j = ~int(c)
+                    if n == 1 and j == 1:  # zero-area dummy sibling of a single-triangle scene
+                        assert np.array_equal(blo, leaf_lo[0]) and np.array_equal(bhi, leaf_hi[0])
+                        continue
                     assert not seen_leaf[j]
                     seen_leaf[j] = True
                     elo, ehi = leaf_lo[j], leaf_hi[j]

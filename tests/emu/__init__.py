@@ -32,7 +32,7 @@ class Emu:
         L.emu_num_nodes.argtypes = [C.c_void_p]
         L.emu_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_float, C.c_float,
-                                C.c_int] + [C.c_void_p] * 7
+                                C.c_int, C.c_int] + [C.c_void_p] * 8
         self.L = L
         self.h = None
 
@@ -47,7 +47,7 @@ class Emu:
         self.free()
         nodes = np.ascontiguousarray(nodes)
         tris = np.ascontiguousarray(tris)
-        self.n = tris.nbytes // 48
+        self.n = tris.nbytes // 64
         self.h = self.L.emu_load(nodes.ctypes.data, nodes.nbytes // 64, tris.ctypes.data, self.n)
         return self
 
@@ -59,11 +59,11 @@ class Emu:
     def download(self):
         nn = self.L.emu_num_nodes(self.h)
         nodes = np.zeros((nn, 16), np.float32)
-        tris = np.zeros((self.n, 12), np.float32)
+        tris = np.zeros((self.n, 16), np.float32)
         self.L.emu_download(self.h, nodes.ctypes.data, tris.ctypes.data)
         return nodes, tris
 
-    def trace(self, rays, prune=1, slack_rel=1e-4, slack_ulps=64.0, anyhit=False):
+    def trace(self, rays, prune=1, slack_rel=1e-4, slack_ulps=64.0, anyhit=False, fast=True):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
         n = len(rays)
         o = {k: np.empty(n, np.float32) for k in ("t", "u", "v")}
@@ -71,10 +71,12 @@ class Emu:
         o["valid"] = np.empty(n, np.uint8)
         p = np.empty((n, 3), np.float32)
         cnt = np.zeros((n, 2), np.uint32)
+        ff = np.zeros(n, np.uint8)
         self.L.emu_trace(self.h, rays.ctypes.data, n, int(prune), slack_rel, slack_ulps,
-                         int(anyhit), o["t"].ctypes.data, o["u"].ctypes.data, o["v"].ctypes.data,
+                         int(anyhit), int(fast), o["t"].ctypes.data, o["u"].ctypes.data, o["v"].ctypes.data,
                          o["pid"].ctypes.data, o["valid"].ctypes.data, p.ctypes.data,
-                         cnt.ctypes.data)
+                         cnt.ctypes.data, ff.ctypes.data)
+        o["fast"] = ff.astype(bool)
         o["valid"] = o["valid"].astype(bool)
         o["px"], o["py"], o["pz"] = (np.ascontiguousarray(p[:, k]) for k in range(3))
         o["counts"] = cnt

@@ -22,6 +22,18 @@ struct Emu {
 	std::vector<Node> nodes;
 	std::vector<TriRec> tris;
 	uint64_t n = 0;
+	float absmax[3] = {0.f, 0.f, 0.f};
+	void bounds() {
+		for (int a = 0; a < 3; ++a)
+			absmax[a] = 0.f;
+		if (nodes.empty())
+			return;
+		const Node &r = nodes[0];
+		for (int a = 0; a < 3; ++a) {
+			absmax[a] = fmaxf(fabsf(r.lo0[a]), fabsf(r.hi0[a]));
+			absmax[a] = fmaxf(absmax[a], fmaxf(fabsf(r.lo1[a]), fabsf(r.hi1[a])));
+		}
+	}
 };
 
 Box refit(Emu &e, const std::vector<Box> &leaf, int32_t ref) {
@@ -89,19 +101,29 @@ void *emu_build(const float *tris9, uint64_t n, int bits) {
 			r.e2[a] = t[6 + a] - t[a];
 		}
 		r.prim = idx[j];
+		r.lox = leaf[j].lo[0];
+		r.loy = leaf[j].lo[1];
+		r.loz = leaf[j].lo[2];
+		r.hix = leaf[j].hi[0];
+		r.hiy = leaf[j].hi[1];
+		r.hiz = leaf[j].hi[2];
 	}
 	if (n == 1) {
 		e->nodes.resize(1);
 		Node &nd = e->nodes[0];
 		std::memset(&nd, 0, sizeof nd);
 		for (int a = 0; a < 3; ++a) {
-			nd.lo0[a] = leaf[0].lo[a];
-			nd.hi0[a] = leaf[0].hi[a];
-			nd.lo1[a] = INFINITY;
-			nd.hi1[a] = -INFINITY;
+			nd.lo0[a] = nd.lo1[a] = leaf[0].lo[a];
+			nd.hi0[a] = nd.hi1[a] = leaf[0].hi[a];
 		}
 		nd.child0 = ~0;
-		nd.child1 = PRT_NO_CHILD;
+		nd.child1 = ~1;
+		TriRec dummy = e->tris[0]; // zero-area: det == 0, never hit
+		for (int a = 0; a < 3; ++a)
+			dummy.e1[a] = dummy.e2[a] = 0.0f;
+		dummy.prim = 0xffffffffu;
+		e->tris.push_back(dummy);
+		e->bounds();
 		return e;
 	}
 	e->nodes.resize(n - 1);
@@ -113,6 +135,7 @@ void *emu_build(const float *tris9, uint64_t n, int bits) {
 		e->nodes[i].child1 = r;
 	}
 	refit(*e, leaf, 0);
+	e->bounds();
 	return e;
 }
 
@@ -123,35 +146,45 @@ void emu_download(void *h, void *nodes, void *tris) {
 	if (nodes && !e->nodes.empty())
 		std::memcpy(nodes, e->nodes.data(), e->nodes.size() * sizeof(Node));
 	if (tris && !e->tris.empty())
-		std::memcpy(tris, e->tris.data(), e->tris.size() * sizeof(TriRec));
+		std::memcpy(tris, e->tris.data(), e->n * sizeof(TriRec));
 }
 // load an externally built tree (e.g. one downloaded from the GPU) for host-side checking
 void *emu_load(const void *nodes, uint64_t n_nodes, const void *tris, uint64_t n_tris) {
 	Emu *e = new Emu();
 	e->n = n_tris;
 	e->nodes.resize(n_nodes);
-	e->tris.resize(n_tris);
+	e->tris.resize(n_tris + 1);
+	std::memset(&e->tris[n_tris], 0, sizeof(TriRec));
 	if (n_nodes)
 		std::memcpy(e->nodes.data(), nodes, n_nodes * sizeof(Node));
 	if (n_tris)
 		std::memcpy(e->tris.data(), tris, n_tris * sizeof(TriRec));
+	e->bounds();
 	return e;
 }
 
 // SoA outputs like the device entry point; counts (2 per ray) may be NULL.  anyhit=1 emulates the
 // `valid`-only specialisation.
 void emu_trace(void *h, const float *rays6, uint64_t n, int prune, float slack_rel, float slack_ulps,
-               int anyhit, float *t, float *u, float *v, uint32_t *pid, uint8_t *valid, float *p,
-               uint32_t *counts) {
+               int anyhit, int fast, float *t, float *u, float *v, uint32_t *pid, uint8_t *valid, float *p,
+               uint32_t *counts, uint8_t *fastflag) {
 	Emu *e = static_cast<Emu *>(h);
 	TraverseOpts o{prune, slack_rel, slack_ulps};
 	for (uint64_t i = 0; i < n; ++i) {
 		RayC r = make_ray(rays6 + 6 * i);
 		Hit hit;
-		if (anyhit)
-			traverse<true, false, false, false>(e->nodes.data(), e->tris.data(), e->n, r, o, hit);
+		const FastRay fr = make_fast_ray(r, e->absmax);
+		const bool f = fast && fr.ok; // per ray here; the kernel votes per warp
+		if (anyhit && f)
+			traverse<true, false, false, false, true>(e->nodes.data(), e->tris.data(), e->n, r, fr, o, hit);
+		else if (anyhit)
+			traverse<true, false, false, false, false>(e->nodes.data(), e->tris.data(), e->n, r, fr, o, hit);
+		else if (f)
+			traverse<false, true, true, true, true>(e->nodes.data(), e->tris.data(), e->n, r, fr, o, hit);
 		else
-			traverse<false, true, true, true>(e->nodes.data(), e->tris.data(), e->n, r, o, hit);
+			traverse<false, true, true, true, false>(e->nodes.data(), e->tris.data(), e->n, r, fr, o, hit);
+		if (fastflag)
+			fastflag[i] = f;
 		if (t)
 			t[i] = hit.t;
 		if (u)
