@@ -1,0 +1,117 @@
+"""Multi-GPU plumbing: rays shard, the scene replicates.
+
+One process per GPU over torch.distributed (NCCL on the GPUs, gloo in the CPU-only tests).  The
+reference has no multi-device path at all (every backend uses device 0); this is the new
+functionality `north_star` asks for: the triangle buffer is broadcast, every rank builds the
+identical BVH, ray i of R goes to rank floor(i*G/R) (contiguous slices whose sizes differ by at
+most one), each rank traces its slice and the hit records come back to rank 0 in ray order.
+There is no collective inside the traversal itself.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def slice_bounds(n: int, world: int, rank: int):
+    """[lo, hi) of rank's contiguous slice: ray i belongs to rank floor(i*world/n)."""
+    lo = -(-rank * n // world)        # ceil(rank*n/world)
+    hi = -(-(rank + 1) * n // world)
+    return lo, hi
+
+
+def owner_of(i: int, n: int, world: int) -> int:
+    return i * world // n
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def broadcast_scene(tris, device, src: int = 0, group=None):
+    """Rank `src` passes its (N,9) float32 triangles, the others pass None; everyone gets a tensor
+    on `device` (36*N bytes over NVLink with NCCL)."""
+    import torch
+    dist = _dist()
+    rank = dist.get_rank(group)
+    n = torch.tensor([0 if tris is None else len(tris)], dtype=torch.int64, device=device)
+    dist.broadcast(n, src=src, group=group)
+    if rank == src:
+        t = torch.as_tensor(np.ascontiguousarray(tris, np.float32)).reshape(-1, 9).to(device)
+    else:
+        t = torch.empty((int(n.item()), 9), dtype=torch.float32, device=device)
+    if t.numel():
+        dist.broadcast(t, src=src, group=group)
+    return t
+
+
+def scatter_rays(rays, device, src: int = 0, group=None):
+    """Rank `src` passes all (R,6) rays; every rank gets (its slice on `device`, R)."""
+    import torch
+    dist = _dist()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n = torch.tensor([0 if rays is None else len(rays)], dtype=torch.int64, device=device)
+    dist.broadcast(n, src=src, group=group)
+    R = int(n.item())
+    width = max(1, -(-R // world))  # equal padded slices for the collective
+    out = torch.zeros((width, 6), dtype=torch.float32, device=device)
+    parts = None
+    if rank == src:
+        full = torch.as_tensor(np.ascontiguousarray(rays, np.float32)).reshape(-1, 6).to(device)
+        parts = []
+        for r in range(world):
+            lo, hi = slice_bounds(R, world, r)
+            p = torch.zeros((width, 6), dtype=torch.float32, device=device)
+            p[: hi - lo] = full[lo:hi]
+            parts.append(p)
+    dist.scatter(out, parts, src=src, group=group)
+    lo, hi = slice_bounds(R, world, rank)
+    return out[: hi - lo].contiguous(), R
+
+
+def gather_device(local, R: int, dst: int = 0, group=None):
+    """local: uint8 tensor (n_local, stride) of this rank's hit records, on the collective's
+    device.  Rank `dst` gets a (R, stride) uint8 tensor in ray order, the others None."""
+    import torch
+    dist = _dist()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    stride = local.shape[1]
+    width = max(1, -(-R // world))
+    if local.shape[0] == width:
+        buf = local.contiguous()
+    else:
+        buf = torch.zeros((width, stride), dtype=torch.uint8, device=local.device)
+        buf[: local.shape[0]] = local
+    parts = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
+    dist.gather(buf, parts, dst=dst, group=group)
+    if rank != dst:
+        return None
+    out = torch.empty((R, stride), dtype=torch.uint8, device=local.device)
+    for r in range(world):
+        lo, hi = slice_bounds(R, world, r)
+        if hi > lo:
+            out[lo:hi] = parts[r][: hi - lo]
+    return out
+
+
+def gather_hits(local_hits: np.ndarray, R: int, device, dst: int = 0, group=None):
+    """local_hits: structured HitReg array of this rank's slice.  Rank `dst` gets the (R,) array in
+    ray order, the others None."""
+    import torch
+    stride = local_hits.dtype.itemsize
+    raw = np.ascontiguousarray(local_hits).view(np.uint8).reshape(len(local_hits), stride)
+    out = gather_device(torch.from_numpy(raw).to(device), R, dst, group)
+    if out is None:
+        return None
+    return out.cpu().numpy().reshape(-1).view(local_hits.dtype).copy()
+
+
+def sharded_nearest_hits(set_tris, trace, tris, rays, device, src: int = 0, group=None):
+    """The whole multi-GPU call: `set_tris(tris_np)` and `trace(rays_np) -> structured hits` are the
+    per-rank backend calls (CUDABackend.set_tris / .nearest_hits bound to this rank's GPU); `tris`
+    and `rays` are given on rank `src` only.  Returns the ray-ordered hits on rank `src`."""
+    t = broadcast_scene(tris, device, src, group)
+    set_tris(t.cpu().numpy())
+    mine, R = scatter_rays(rays, device, src, group)
+    hits = trace(mine.cpu().numpy())
+    return gather_hits(hits, R, device, src, group)
