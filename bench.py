@@ -39,7 +39,7 @@ sys.path.insert(0, ROOT)
 
 
 # ------------------------------------------------------------------------------------------------
-def workload(name: str, frame: int = 0):
+def workload(name: str, frame: int = 0, tracer=None):
     """-> (tris (N,9) f32, rays (R,6) f32, mask, description)"""
     from portablert_b200 import hitreg, scenes
     if name == "c2":
@@ -53,6 +53,17 @@ def workload(name: str, frame: int = 0):
         rays = scenes.camera_rays(3840, 2160, (2 + 0.01 * frame, 6, 3), (28, 4, 15))
         return tris, rays, hitreg.ALL, ("C3: %d-tri interior, 3840x2160 primary rays, all tags"
                                         % len(tris))
+    if name == "c3b":
+        # one-bounce incoherent diffuse rays spawned at the primary hits of C3 (the primary hits
+        # are input preparation: `tracer(tris, rays) -> full hit records` runs before any timing)
+        tris = scenes.interior()
+        prim = scenes.camera_rays(3840, 2160, (2 + 0.01 * frame, 6, 3), (28, 4, 15))
+        h = tracer(tris, prim)
+        p = np.stack([h["px"], h["py"], h["pz"]], -1)
+        rays, _ = scenes.bounce_rays(tris, prim, h["valid"], h["primitive_id"], p)
+        return tris, rays, hitreg.T | hitreg.PID, ("C3 bounce: %d-tri interior, %d one-bounce "
+                                                   "cosine-weighted diffuse rays, t+primitive_id"
+                                                   % (len(tris), len(rays)))
     if name == "c5":
         tris = scenes.heightfield(frame)
         rays = scenes.camera_rays(3840, 2160, (10, 6, -4), (10, 0, 5))[:8_000_000]
@@ -146,6 +157,7 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+_JSON_OUT = sys.stdout
 OUT_BYTES = {1: 8, 2: 4, 4: 4, 8: 12, 16: 1}
 
 
@@ -187,7 +199,13 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    tris, rays, mask, desc = workload(args.config)
+    def ref_tracer(t, r):
+        from oracle import Reference
+        ref = Reference()
+        ref.set_tris(t)
+        return ref.nearest_hits(r, 31)
+
+    tris, rays, mask, desc = workload(args.config, tracer=ref_tracer)
     cb = cpu_reference(tris, rays, mask, budget_s=60.0, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": "nearest_hits throughput", "value": cb["value"],
@@ -201,7 +219,7 @@ def run_reference_arm(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -215,6 +233,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--per-mask", action="store_true", help="also time all 31 tag masks")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: keep a private handle to it and send everything else
+    # that libraries print to fd 1 (e.g. NCCL's version banner) to stderr
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":
@@ -239,7 +262,11 @@ def main():
     prt.select_backend(backend)
 
     # ---- inputs: rank 0 owns the scene; triangles are broadcast, each rank gets its ray slice
-    tris, rays, mask, desc = workload(args.config, frame=rank)
+    def gpu_tracer(t, r):
+        backend.set_tris(t)
+        return backend.nearest_hits(r)
+
+    tris, rays, mask, desc = workload(args.config, frame=rank, tracer=gpu_tracer)
     if world > 1:
         d_tris = torch.from_numpy(tris).to(dev) if rank == 0 else torch.empty(tris.shape, device=dev)
         dist.broadcast(d_tris, src=0)  # 36*N bytes over NVLink
@@ -311,15 +338,27 @@ def main():
     e2e_steps = max(3, min(args.steps, 10))
     if world == 1:
         # the reference-facing call itself: prt_b200_nearest_hits(host rays) -> host AoS records
+        # (a) inputs in pinned host memory, result array reused: what the contract asks for
+        from portablert_b200.backend import pinned_empty
+        p_rays = pinned_empty(rays.shape, np.float32)
+        p_rays[...] = rays
+        p_hits = pinned_empty((n_rays,), hitreg.dtype(mask))
         for _ in range(2):
-            backend.nearest_hits(rays, mask)
+            backend.nearest_hits(p_rays, mask, out=p_hits)
         barrier()
         e2e_t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            hits = backend.nearest_hits(rays, mask)
+            hits = backend.nearest_hits(p_rays, mask, out=p_hits)
         barrier()
         e2e_s = (time.perf_counter() - e2e_t0) / e2e_steps
-        api = "prt_b200_nearest_hits (host rays -> host HitReg AoS)"
+        # (b) pageable numpy in, fresh array out (what std::vector callers of the C++ API get)
+        for _ in range(2):
+            backend.nearest_hits(rays, mask)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            hits = backend.nearest_hits(rays, mask)
+        e2e_pageable_s = (time.perf_counter() - t0) / e2e_steps
+        api = "prt_b200_nearest_hits (pinned host rays -> pinned host HitReg AoS, 2-stream chunks)"
     else:
         # rank 0 owns the whole N-frame batch on the host: one H2D on rank 0, NCCL scatter of the
         # contiguous slices, per-rank traversal writing AoS records on the device, NCCL gather in
@@ -327,16 +366,21 @@ def main():
         from portablert_b200 import sharding
         all_rays = None
         if rank == 0:
-            all_rays = np.concatenate([rays] + [workload(args.config, frame=r)[1]
-                                                for r in range(1, world)])
+            all_rays = torch.from_numpy(np.concatenate(
+                [rays] + [workload(args.config, frame=r, tracer=gpu_tracer)[1]
+                          for r in range(1, world)])).pin_memory()
         d_hits = torch.empty((n_rays, stride), dtype=torch.uint8, device=dev)
+        h_hits = torch.empty((total_rays, stride), dtype=torch.uint8).pin_memory() if rank == 0 \
+            else None
 
         def e2e_step():
             mine, R = sharding.scatter_rays(all_rays, dev)
             torch.cuda.synchronize()
             backend.trace_dev_aos(mine.data_ptr(), len(mine), mask, d_hits.data_ptr())
             out = sharding.gather_device(d_hits[: len(mine)], R)
-            return out.cpu() if out is not None else None
+            if out is not None:
+                h_hits.copy_(out, non_blocking=True)
+                torch.cuda.synchronize()
 
         for _ in range(2):
             e2e_step()
@@ -354,6 +398,10 @@ def main():
     e2e = {"value": total_rays / e2e_s / 1e6, "unit": "Mrays/s",
            "h2d_bytes_per_step": 24 * total_rays, "d2h_bytes_per_step": stride * total_rays,
            "ms_per_step": e2e_s * 1e3, "api": api}
+    if world == 1:
+        e2e["pageable_value"] = total_rays / e2e_pageable_s / 1e6
+        e2e["pageable_note"] = ("same call with pageable numpy input and a freshly allocated "
+                                "result (staged through pinned buffers by threaded memcpy)")
 
     if rank != 0:
         if world > 1:
@@ -438,7 +486,7 @@ def main():
     }
     if per_mask:
         line["per_mask_mrays_s"] = per_mask
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -103,6 +103,12 @@ int prt_b200_set_tris_dev(prt_b200 *ctx, const float *d_tris9, uint64_t n_tris, 
 int prt_b200_nearest_hits(prt_b200 *ctx, const float *rays6, uint64_t n_rays, uint32_t tag_mask,
                           const prt_hit_layout *layout, void *hits_out);
 
+/* Page-locked host memory.  prt_b200_set_tris / prt_b200_nearest_hits detect pinned (or
+ * cudaHostRegister'ed) buffers and DMA from/to them directly; pageable memory (e.g. a plain
+ * std::vector, as in the reference API) is staged through internal pinned buffers. */
+void *prt_b200_alloc_pinned(size_t bytes);
+void prt_b200_free_pinned(void *p);
+
 /* Device-resident traversal for device-timed measurement: rays and outputs live on the context's
  * device.  *trace_ms (may be NULL) = device time of the traversal kernel(s), CUDA events on the
  * context's stream.  Fields not in tag_mask are not written (and may be NULL). */

@@ -53,6 +53,8 @@ SYMBOLS = {
     "prt_b200_last_trace_ms": (C.c_float, [C.c_void_p]),
     "prt_b200_download_bvh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "prt_b200_read_bandwidth": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
+    "prt_b200_alloc_pinned": (C.c_void_p, [C.c_size_t]),
+    "prt_b200_free_pinned": (None, [C.c_void_p]),
     "prt_b200_last_error": (C.c_char_p, [C.c_void_p]),
 }
 

@@ -103,12 +103,19 @@ class CUDABackend(Backend):
         self._check(lib().prt_b200_set_tris(self._h, tris.ctypes.data, len(tris)))
 
     # --- nearest_hits<Tags...> ------------------------------------------------------------------
-    def nearest_hits(self, rays, *tags):
-        """Host rays (R,6) float32 -> structured array of HitReg<tags...> (all tags when none given)."""
+    def nearest_hits(self, rays, *tags, out=None):
+        """Host rays (R,6) float32 -> structured array of HitReg<tags...> (all tags when none given).
+        `out` (optional) is a preallocated result array, e.g. from pinned_empty(), to be reused."""
         self._need()
         mask = hitreg.mask_of(tags[0] if len(tags) == 1 and not isinstance(tags[0], str) else tags)
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
-        hits = np.zeros(len(rays), hitreg.dtype(mask))
+        if out is None:
+            hits = np.zeros(len(rays), hitreg.dtype(mask))
+        else:
+            hits = out
+            if hits.dtype != hitreg.dtype(mask) or len(hits) != len(rays) or \
+                    not hits.flags["C_CONTIGUOUS"]:
+                raise ValueError("out must be a contiguous HitReg array of len(rays) for these tags")
         lay = _layout_struct(mask)
         self._check(lib().prt_b200_nearest_hits(self._h, rays.ctypes.data, len(rays), mask,
                                                 C.byref(lay), hits.ctypes.data))
@@ -202,6 +209,29 @@ class CUDABackend(Backend):
             self.shutdown()
         except Exception:
             pass
+
+
+class _Pinned:
+    def __init__(self, nbytes):
+        self.ptr = lib().prt_b200_alloc_pinned(nbytes)
+        if not self.ptr:
+            raise MemoryError(f"cudaMallocHost({nbytes}) failed")
+        self.buf = (C.c_char * max(1, nbytes)).from_address(self.ptr)
+
+    def __del__(self):
+        try:
+            lib().prt_b200_free_pinned(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """numpy array in page-locked host memory (the host entry points then DMA directly)."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    owner = _Pinned(n)
+    owner.buf._prt_owner = owner  # arr.base -> ctypes buffer -> owner: freed with the last view
+    return np.frombuffer(owner.buf, dtype=np.uint8, count=n).view(dt).reshape(shape)
 
 
 # --- registry (backend.hpp:39-46, 83-95; src/backend.cpp:50-56) --------------------------------

@@ -269,10 +269,46 @@ int prt_b200_trace_count_dev(prt_b200 *c, const float *d_rays6, uint64_t n, uint
 	return timed_trace(c, d_rays6, n, PRT_TAG_ALL, out, d_counts, nullptr);
 }
 
-// Host-pointer entry point.  Rays are cut into chunks; each chunk goes pageable -> pinned (host
-// memcpy) -> device (async H2D) -> traversal kernel writing the caller's AoS records -> pinned
-// (async D2H) -> the caller's buffer.  Two buffer sets alternate so the copies of chunk k+1
-// overlap the traversal of chunk k.
+// ---- host-pointer entry point -------------------------------------------------------------------
+static bool is_pinned(const void *p) {
+	cudaPointerAttributes a{};
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return a.type == cudaMemoryTypeHost;
+}
+
+// memcpy split over a few host threads: staging 50-100 MB through one core would cost more than
+// the PCIe transfer and the traversal together
+static void par_memcpy(void *dst, const void *src, size_t bytes) {
+	const size_t MIN_PER_THREAD = 2u << 20;
+	unsigned hw = std::thread::hardware_concurrency();
+	size_t nt = std::min<size_t>(std::min<size_t>(hw ? hw : 1, 8), bytes / MIN_PER_THREAD);
+	if (nt <= 1) {
+		std::memcpy(dst, src, bytes);
+		return;
+	}
+	std::vector<std::thread> th;
+	const size_t per = (bytes / nt + 63) & ~size_t(63);
+	for (size_t k = 1; k < nt; ++k) {
+		const size_t off = k * per;
+		if (off >= bytes)
+			break;
+		th.emplace_back([=] {
+			std::memcpy(static_cast<char *>(dst) + off, static_cast<const char *>(src) + off,
+			            std::min(per, bytes - off));
+		});
+	}
+	std::memcpy(dst, src, std::min(per, bytes));
+	for (auto &t : th)
+		t.join();
+}
+
+// Rays are cut into chunks; chunk k runs on stream k&1: H2D -> traversal kernel writing the
+// caller's AoS records -> D2H, so the copies of one chunk overlap the traversal of the other.
+// Pageable host memory (a std::vector) is staged through pinned buffers with a threaded memcpy;
+// pinned / registered host memory is DMA'd directly.
 int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t mask,
                           const prt_hit_layout *layout, void *hits_out) {
 	if (!c || (n && (!rays6 || !hits_out)))
@@ -285,54 +321,80 @@ int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t 
 		return PRT_OK;
 	PRT_CUDA(c, cudaSetDevice(c->device));
 
-	const uint64_t CH = std::min<uint64_t>(n, 1ull << 20);
+	const bool in_pinned = is_pinned(rays6), out_pinned = is_pinned(hits_out);
+	const uint64_t CH = std::min<uint64_t>(n, 1ull << 19);
 	const size_t ray_b = 24, hit_b = layout->stride;
 	for (int k = 0; k < 2; ++k) {
 		PRT_CUDA(c, c->rays_dev[k].reserve(CH * ray_b));
 		PRT_CUDA(c, c->hits_dev[k].reserve(CH * hit_b));
-		PRT_CUDA(c, c->rays_pin[k].reserve(CH * ray_b));
-		PRT_CUDA(c, c->hits_pin[k].reserve(CH * hit_b));
+		if (!in_pinned)
+			PRT_CUDA(c, c->rays_pin[k].reserve(CH * ray_b));
+		if (!out_pinned)
+			PRT_CUDA(c, c->hits_pin[k].reserve(CH * hit_b));
 	}
 	const uint64_t n_chunks = (n + CH - 1) / CH;
-	PRT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-	// software pipeline over chunks: stage(k) | trace(k-1) | drain(k-2)
-	for (uint64_t k = 0; k < n_chunks + 1; ++k) {
-		if (k < n_chunks) {
-			const int b = (int)(k & 1);
-			const uint64_t first = k * CH, cnt = std::min(CH, n - first);
-			if (k >= 2) {
-				// buffer set b was last used by chunk k-2: wait for its D2H, hand the hits over
-				PRT_CUDA(c, cudaEventSynchronize(c->ev_chunk[b][1]));
-				const uint64_t pf = (k - 2) * CH, pc = std::min(CH, n - pf);
-				std::memcpy(static_cast<char *>(hits_out) + pf * hit_b, c->hits_pin[b].p, pc * hit_b);
-			}
-			std::memcpy(c->rays_pin[b].p, rays6 + first * 6, cnt * ray_b);
-			PRT_CUDA(c, cudaMemcpyAsync(c->rays_dev[b].p, c->rays_pin[b].p, cnt * ray_b,
-			                            cudaMemcpyHostToDevice, c->stream));
-			prt::TraceOut out;
-			out.aos = c->hits_dev[b].p;
-			out.layout = *layout;
-			int rc = prt::launch_trace(c, c->rays_dev[b].as<float>(), cnt, mask, out, nullptr,
-			                           c->stream);
-			if (rc)
-				return rc;
-			PRT_CUDA(c, cudaMemcpyAsync(c->hits_pin[b].p, c->hits_dev[b].p, cnt * hit_b,
-			                            cudaMemcpyDeviceToHost, c->stream));
-			PRT_CUDA(c, cudaEventRecord(c->ev_chunk[b][1], c->stream));
+	auto drain = [&](uint64_t k) -> cudaError_t { // chunk k's D2H is done: hand the records over
+		const int b = (int)(k & 1);
+		cudaError_t e = cudaEventSynchronize(c->ev_chunk[b][1]);
+		if (e == cudaSuccess && !out_pinned) {
+			const uint64_t pf = k * CH, pc = std::min(CH, n - pf);
+			par_memcpy(static_cast<char *>(hits_out) + pf * hit_b, c->hits_pin[b].p, pc * hit_b);
 		}
+		return e;
+	};
+	// the context stream marks the start; both chunk streams wait for it (the BVH build ran there)
+	PRT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+	for (int k = 0; k < 2; ++k)
+		PRT_CUDA(c, cudaStreamWaitEvent(c->copy_stream[k], c->ev0, 0));
+	for (uint64_t k = 0; k < n_chunks; ++k) {
+		const int b = (int)(k & 1);
+		cudaStream_t s = c->copy_stream[b];
+		const uint64_t first = k * CH, cnt = std::min(CH, n - first);
+		if (k >= 2)
+			PRT_CUDA(c, drain(k - 2)); // buffer set b is free again
+		const void *src = rays6 + first * 6;
+		if (!in_pinned) {
+			par_memcpy(c->rays_pin[b].p, src, cnt * ray_b);
+			src = c->rays_pin[b].p;
+		}
+		PRT_CUDA(c, cudaMemcpyAsync(c->rays_dev[b].p, src, cnt * ray_b, cudaMemcpyHostToDevice, s));
+		prt::TraceOut out;
+		out.aos = c->hits_dev[b].p;
+		out.layout = *layout;
+		out.slot = b;
+		int rc = prt::launch_trace(c, c->rays_dev[b].as<float>(), cnt, mask, out, nullptr, s);
+		if (rc)
+			return rc;
+		void *dst = out_pinned ? static_cast<void *>(static_cast<char *>(hits_out) + first * hit_b)
+		                       : c->hits_pin[b].p;
+		PRT_CUDA(c, cudaMemcpyAsync(dst, c->hits_dev[b].p, cnt * hit_b, cudaMemcpyDeviceToHost, s));
+		PRT_CUDA(c, cudaEventRecord(c->ev_chunk[b][1], s));
+	}
+	for (uint64_t k = n_chunks >= 2 ? n_chunks - 2 : 0; k < n_chunks; ++k)
+		PRT_CUDA(c, drain(k));
+	// join the chunk streams back into the context stream and time the whole call on the device
+	for (int k = 0; k < 2; ++k) {
+		PRT_CUDA(c, cudaEventRecord(c->ev_chunk[k][0], c->copy_stream[k]));
+		PRT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_chunk[k][0], 0));
 	}
 	PRT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
-	// drain the last (up to) two chunks
-	const uint64_t first_pending = n_chunks >= 2 ? n_chunks - 2 : 0;
-	for (uint64_t k = first_pending; k < n_chunks; ++k) {
-		const int b = (int)(k & 1);
-		PRT_CUDA(c, cudaEventSynchronize(c->ev_chunk[b][1]));
-		const uint64_t pf = k * CH, pc = std::min(CH, n - pf);
-		std::memcpy(static_cast<char *>(hits_out) + pf * hit_b, c->hits_pin[b].p, pc * hit_b);
-	}
 	PRT_CUDA(c, cudaStreamSynchronize(c->stream));
 	PRT_CUDA(c, cudaEventElapsedTime(&c->last_trace_ms, c->ev0, c->ev1));
 	return PRT_OK;
+}
+
+// Pinned host memory for callers that want the host entry points to DMA directly (no staging).
+void *prt_b200_alloc_pinned(size_t bytes) {
+	void *p = nullptr;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	return p;
+}
+void prt_b200_free_pinned(void *p) {
+	if (p)
+		cudaFreeHost(p);
 }
 
 // Bandwidth probe: a persistent grid repeatedly reads `bytes` of device memory with 16-byte

@@ -94,7 +94,7 @@ struct prt_b200 {
 
 	float scene_absmax[3] = {0.f, 0.f, 0.f}; // largest |coordinate| per axis (fast box-test margin)
 	int fast_boxes = 1;                      // env PRT_B200_FAST_BOXES=0 forces the exact test everywhere
-	int refill = 24;                         // env PRT_B200_REFILL: dynamic ray-fetch threshold (lanes)
+	int refill = 16;                         // env PRT_B200_REFILL: dynamic ray-fetch threshold (lanes)
 	uint64_t launches = 0;
 	float last_build_ms = 0.f, last_trace_ms = 0.f;
 };
@@ -128,6 +128,7 @@ struct TraceOut {
 	prt_soa_out soa{};
 	void *aos = nullptr;
 	prt_hit_layout layout{};
+	int slot = 0; // which ray counter to use (concurrent launches on different streams)
 };
 int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, const TraceOut &out,
                  uint32_t *d_counts, cudaStream_t stream);

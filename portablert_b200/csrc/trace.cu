@@ -221,7 +221,7 @@ int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, c
 	P.fast = c->fast_boxes;
 	P.refill = c->refill;
 	PRT_CUDA(c, c->counter.reserve(256));
-	P.counter = c->counter.as<unsigned long long>();
+	P.counter = c->counter.as<unsigned long long>() + 2 * out.slot; // 16 bytes apart
 	PRT_CUDA(c, cudaMemsetAsync(P.counter, 0, 8, s));
 
 	const bool aos = out.aos != nullptr;
@@ -264,7 +264,7 @@ int launch_read_probe(prt_b200 *c, const void *buf, uint64_t bytes, int iters, f
 	PRT_CUDA(c, c->counter.reserve(256));
 	PRT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
 	k_read_probe<<<c->sm_count * 8, 256, 0, c->stream>>>(static_cast<const uint4 *>(buf), bytes / 16,
-	                                                     iters, c->counter.as<uint32_t>() + 8);
+	                                                     iters, c->counter.as<uint32_t>() + 32);
 	c->launches += 1;
 	PRT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
 	PRT_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -50,20 +50,27 @@ def scatter_rays(rays, device, src: int = 0, group=None):
     import torch
     dist = _dist()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    n = torch.tensor([0 if rays is None else len(rays)], dtype=torch.int64, device=device)
+    n_here = 0 if rays is None else (rays.numel() // 6 if isinstance(rays, torch.Tensor) else len(rays))
+    n = torch.tensor([n_here], dtype=torch.int64, device=device)
     dist.broadcast(n, src=src, group=group)
     R = int(n.item())
     width = max(1, -(-R // world))  # equal padded slices for the collective
     out = torch.zeros((width, 6), dtype=torch.float32, device=device)
     parts = None
     if rank == src:
-        full = torch.as_tensor(np.ascontiguousarray(rays, np.float32)).reshape(-1, 6).to(device)
+        if isinstance(rays, torch.Tensor):  # e.g. a pinned host tensor: one DMA, no staging
+            full = rays.reshape(-1, 6).to(device, non_blocking=True)
+        else:
+            full = torch.as_tensor(np.ascontiguousarray(rays, np.float32)).reshape(-1, 6).to(device)
         parts = []
         for r in range(world):
             lo, hi = slice_bounds(R, world, r)
-            p = torch.zeros((width, 6), dtype=torch.float32, device=device)
-            p[: hi - lo] = full[lo:hi]
-            parts.append(p)
+            if hi - lo == width:
+                parts.append(full[lo:hi])  # equal slices: views, no copy
+            else:
+                p = torch.zeros((width, 6), dtype=torch.float32, device=device)
+                p[: hi - lo] = full[lo:hi]
+                parts.append(p)
     dist.scatter(out, parts, src=src, group=group)
     lo, hi = slice_bounds(R, world, rank)
     return out[: hi - lo].contiguous(), R
@@ -82,11 +89,16 @@ def gather_device(local, R: int, dst: int = 0, group=None):
     else:
         buf = torch.zeros((width, stride), dtype=torch.uint8, device=local.device)
         buf[: local.shape[0]] = local
-    parts = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
-    dist.gather(buf, parts, dst=dst, group=group)
     if rank != dst:
+        dist.gather(buf, None, dst=dst, group=group)
         return None
     out = torch.empty((R, stride), dtype=torch.uint8, device=local.device)
+    if R == width * world:  # equal slices: receive straight into the ray-ordered result
+        parts = [out[r * width:(r + 1) * width] for r in range(world)]
+        dist.gather(buf, parts, dst=dst, group=group)
+        return out
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.gather(buf, parts, dst=dst, group=group)
     for r in range(world):
         lo, hi = slice_bounds(R, world, r)
         if hi > lo:
