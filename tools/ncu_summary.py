@@ -66,10 +66,12 @@ def main():
             if k in vals and vals[k] != "":
                 print(f"| {label} (`{k}`) | {vals[k]} | {units.get(k, '')} |")
         try:
-            rd = float(vals["dram__bytes_read.sum"].replace(",", ""))
-            wr = float(vals["dram__bytes_write.sum"].replace(",", ""))
-            u = units.get("dram__bytes_read.sum", "")
-            print(f"\nDRAM traffic (read + write) per launch: {rd + wr:.3f} {u}\n")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+            rd = float(vals["dram__bytes_read.sum"].replace(",", "")) * \
+                scale[units.get("dram__bytes_read.sum", "byte")]
+            wr = float(vals["dram__bytes_write.sum"].replace(",", "")) * \
+                scale[units.get("dram__bytes_write.sum", "byte")]
+            print(f"\nDRAM traffic (read + write) per launch: {(rd + wr) / 1e6:.3f} MB\n")
         except Exception:
             print()
 
