@@ -123,6 +123,13 @@ int prt_b200_trace_dev_aos(prt_b200 *ctx, const float *d_rays6, uint64_t n_rays,
 /* Traversal knobs; opts == NULL restores the defaults. */
 int prt_b200_set_trace_opts(prt_b200 *ctx, const prt_trace_opts *opts);
 
+/* Ray reordering in front of the traversal (results keep the caller's ray order): 0 = never,
+ * 1 = always, 2 = automatic (default; env PRT_B200_SORT_RAYS): batches of >= 65 536 rays are
+ * sorted by a 24-bit origin/direction key unless most neighbouring rays already share their key.
+ * prt_b200_sorted_batches counts the launches that were actually reordered. */
+int prt_b200_set_ray_sorting(prt_b200 *ctx, int mode);
+uint64_t prt_b200_sorted_batches(const prt_b200 *ctx);
+
 /* Instrumented traversal (never used in timed runs): per ray, counts[2i] = internal nodes
  * fetched, counts[2i+1] = triangles tested; feeds the bytes/ray figure of the roofline
  * (SURVEY.md 8d).  d_counts: device pointer to 2*n_rays uint32. */

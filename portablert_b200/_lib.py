@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libprt_b200.so")
+# PRT_B200_LIB: alternative build of the same library (A/B experiments); default = the in-tree one
+LIB_PATH = os.environ.get("PRT_B200_LIB") or os.path.join(HERE, "libprt_b200.so")
 
 OK, E_NO_DEVICE, E_CUDA, E_ARG, E_OOM, E_LIMIT = range(6)
 
@@ -44,6 +45,8 @@ SYMBOLS = {
     "prt_b200_trace_dev_aos": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
                                          C.POINTER(HitLayout), C.c_void_p, C.POINTER(C.c_float)]),
     "prt_b200_set_trace_opts": (C.c_int, [C.c_void_p, C.POINTER(TraceOpts)]),
+    "prt_b200_set_ray_sorting": (C.c_int, [C.c_void_p, C.c_int]),
+    "prt_b200_sorted_batches": (C.c_uint64, [C.c_void_p]),
     "prt_b200_trace_count_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "prt_b200_num_tris": (C.c_uint64, [C.c_void_p]),
     "prt_b200_num_nodes": (C.c_uint64, [C.c_void_p]),

@@ -154,6 +154,15 @@ class CUDABackend(Backend):
         o = TraceOpts(int(prune), float(slack_rel), float(slack_ulps))
         self._check(lib().prt_b200_set_trace_opts(self._h, C.byref(o)))
 
+    def set_ray_sorting(self, mode: int):
+        """0 never, 1 always, 2 automatic (default): reorder incoherent batches before traversal."""
+        self._need()
+        self._check(lib().prt_b200_set_ray_sorting(self._h, int(mode)))
+
+    @property
+    def sorted_batches(self):
+        return lib().prt_b200_sorted_batches(self._h)
+
     def read_bandwidth(self, nbytes: int, iters: int = 20) -> float:
         self._need()
         g = C.c_float()

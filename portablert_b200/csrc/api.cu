@@ -86,6 +86,12 @@ int prt_b200_create(prt_b200 **out, int device) {
 	for (int k = 0; k < 2 && e == cudaSuccess; ++k)
 		for (int j = 0; j < 2 && e == cudaSuccess; ++j)
 			e = cudaEventCreateWithFlags(&c->ev_chunk[k][j], cudaEventDisableTiming);
+	if (e == cudaSuccess)
+		e = cudaHostAlloc(reinterpret_cast<void **>(&c->probe_host), 64, cudaHostAllocMapped);
+	if (e == cudaSuccess)
+		e = cudaHostGetDevicePointer(reinterpret_cast<void **>(&c->probe_dev), c->probe_host, 0);
+	if (e == cudaSuccess)
+		e = c->probe_ticket.reserve(64);
 	if (e != cudaSuccess) {
 		g_create_err = std::string("create: ") + cudaGetErrorString(e);
 		prt_b200_destroy(c);
@@ -94,6 +100,8 @@ int prt_b200_create(prt_b200 **out, int device) {
 	c->sm_count = prop.multiProcessorCount;
 	if (const char *e = std::getenv("PRT_B200_FAST_BOXES"))
 		c->fast_boxes = std::atoi(e) != 0;
+	if (const char *e = std::getenv("PRT_B200_SORT_RAYS"))
+		c->sort_rays = std::max(0, std::min(2, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_REFILL"))
 		c->refill = std::max(0, std::min(32, std::atoi(e)));
 	c->name = prop.name;
@@ -109,12 +117,22 @@ void prt_b200_destroy(prt_b200 *c) {
 	if (c->stream)
 		cudaStreamSynchronize(c->stream);
 	prt::DevBuf *bufs[] = {&c->tris_raw, &c->nodes,    &c->trirecs,     &c->keys[0],     &c->keys[1],
-	                       &c->vals[0],  &c->vals[1],  &c->counts,      &c->totals,      &c->bounds,
+	                       &c->vals[0],  &c->vals[1],  &c->sort_scratch, &c->bounds,
 	                       &c->leaf_box, &c->node_box, &c->parent,      &c->leaf_parent, &c->flags,
 	                       &c->rays_dev[0], &c->rays_dev[1], &c->hits_dev[0], &c->hits_dev[1],
 	                       &c->counter};
 	for (auto *b : bufs)
 		b->release();
+	c->probe_ticket.release();
+	if (c->probe_host)
+		cudaFreeHost(c->probe_host);
+	for (auto &r : c->rs) {
+		r.keys[0].release();
+		r.keys[1].release();
+		r.vals[0].release();
+		r.vals[1].release();
+		r.scratch.release();
+	}
 	for (int k = 0; k < 2; ++k) {
 		c->rays_pin[k].release();
 		c->hits_pin[k].release();
@@ -140,6 +158,14 @@ int prt_b200_device_name(const prt_b200 *c, char *buf, size_t cap) {
 	buf[cap - 1] = 0;
 	return (int)std::min(c->name.size(), cap - 1);
 }
+
+int prt_b200_set_ray_sorting(prt_b200 *c, int mode) {
+	if (!c || mode < 0 || mode > 2)
+		return fail(c, PRT_E_ARG, "set_ray_sorting: mode must be 0, 1 or 2");
+	c->sort_rays = mode;
+	return PRT_OK;
+}
+uint64_t prt_b200_sorted_batches(const prt_b200 *c) { return c ? c->sorted_batches : 0; }
 
 int prt_b200_set_trace_opts(prt_b200 *c, const prt_trace_opts *o) {
 	if (!c)
@@ -171,6 +197,8 @@ static int timed_build(prt_b200 *c, const float *d_tris9, uint64_t n, float *ms)
 			m = std::max(m, std::max(std::fabs(root.lo1[a]), std::fabs(root.hi1[a])));
 		}
 		c->scene_absmax[a] = m;
+		c->scene_lo[a] = c->n_nodes ? std::min(root.lo0[a], root.lo1[a]) : 0.f;
+		c->scene_hi[a] = c->n_nodes ? std::max(root.hi0[a], root.hi1[a]) : 0.f;
 	}
 	if (ms)
 		*ms = c->last_build_ms;

@@ -4,8 +4,9 @@
 // reached from CPUBackend::set_tris, src/intersect_cpu.cpp:12) with a data-parallel build:
 //   1 bounds    coalesced float4 tile loads -> per-triangle AABB -> centroid bounds (atomics)
 //   2 morton    3*b-bit Morton key of the AABB centre (b = 10/16/21 bits per axis) + identity index
-//   3 sort      LSD radix sort, 8-bit digits, (u64 key, u32 index), tiles ranked in shared memory
-//               with warp-level match/prefix ranking, coalesced scatter
+//   3 sort      LSD radix sort (sort.cu): 8-bit digits, (u64 key, u32 index), one kernel per pass,
+//               tiles ranked in shared memory with warp-level match/prefix operations,
+//               decoupled look-back for the global offsets, coalesced scatter
 //   4 karras    one thread per internal node: range + split (Karras 2012), parent links
 //   5 leaves    gather triangles into Morton order as 64-byte records (v0, edges, own AABB)
 //   6 refit     bottom-up, second-arriver-continues with one atomic counter per node; writes the
@@ -152,186 +153,7 @@ __global__ void __launch_bounds__(TT) k_morton(const float *__restrict__ tris9, 
 	}
 }
 
-// ------------------------------------------------------------------------------------------------
-// 3. LSD radix sort: 8-bit digits, u64 keys, u32 values
-// ------------------------------------------------------------------------------------------------
-constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS = 8;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
-constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RADIX = 256;
-
-// per-tile digit histogram -> counts[digit * n_tiles + tile]; also accumulates totals[digit]
-__global__ void __launch_bounds__(RS_THREADS)
-    k_sort_hist(const uint64_t *__restrict__ keys, uint64_t n, int shift,
-                uint32_t *__restrict__ counts, uint32_t *__restrict__ totals, uint32_t n_tiles) {
-	__shared__ uint32_t hist[RADIX];
-	hist[threadIdx.x] = 0;
-	__syncthreads();
-	const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
-#pragma unroll
-	for (int k = 0; k < RS_ITEMS; ++k) {
-		const uint64_t i = base + (uint64_t)k * RS_THREADS + threadIdx.x;
-		const bool ok = i < n;
-		const uint32_t d = ok ? (uint32_t)((keys[i] >> shift) & 0xff) : 256u;
-		const uint32_t peers = __match_any_sync(0xffffffffu, d);
-		if (ok && (threadIdx.x & 31) == (__ffs(peers) - 1))
-			atomicAdd(&hist[d], __popc(peers));
-	}
-	__syncthreads();
-	const uint32_t c = hist[threadIdx.x];
-	counts[(uint64_t)threadIdx.x * n_tiles + blockIdx.x] = c;
-	if (c)
-		atomicAdd(&totals[threadIdx.x], c);
-}
-
-// block-wide exclusive scan of one value per thread (RS_THREADS threads); returns exclusive prefix,
-// *total = block sum.
-__device__ __forceinline__ uint32_t block_exscan(uint32_t v, uint32_t *warp_sums, uint32_t *total) {
-	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	uint32_t inc = v;
-#pragma unroll
-	for (int o = 1; o < 32; o <<= 1) {
-		uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-		if (lane >= o)
-			inc += t;
-	}
-	if (lane == 31)
-		warp_sums[w] = inc;
-	__syncthreads();
-	if (w == 0) {
-		uint32_t s = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
-		uint32_t si = s;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			uint32_t t = __shfl_up_sync(0xffffffffu, si, o);
-			if (lane >= o)
-				si += t;
-		}
-		warp_sums[lane] = si - s; // exclusive
-		if (lane == 31)
-			warp_sums[32] = si;
-	}
-	__syncthreads();
-	const uint32_t res = warp_sums[w] + inc - v;
-	if (total)
-		*total = warp_sums[32];
-	__syncthreads();
-	return res;
-}
-
-// one block per digit: exclusive scan over that digit's per-tile counts, in place
-__global__ void __launch_bounds__(RS_THREADS) k_sort_scan(uint32_t *__restrict__ counts,
-                                                          uint32_t n_tiles) {
-	__shared__ uint32_t ws[33];
-	uint32_t *row = counts + (uint64_t)blockIdx.x * n_tiles;
-	uint32_t carry = 0;
-	for (uint32_t base = 0; base < n_tiles; base += RS_THREADS) {
-		const uint32_t i = base + threadIdx.x;
-		const uint32_t v = i < n_tiles ? row[i] : 0;
-		uint32_t tot;
-		const uint32_t ex = block_exscan(v, ws, &tot);
-		if (i < n_tiles)
-			row[i] = carry + ex;
-		carry += tot;
-	}
-}
-
-__global__ void __launch_bounds__(RS_THREADS)
-    k_sort_scatter(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                   uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint64_t n,
-                   int shift, const uint32_t *__restrict__ counts,
-                   const uint32_t *__restrict__ totals, uint32_t n_tiles) {
-	__shared__ uint64_t s_keys[RS_TILE];
-	__shared__ uint32_t s_vals[RS_TILE];
-	__shared__ uint32_t wh[RS_WARPS][RADIX];
-	__shared__ uint32_t lbase[RADIX];
-	__shared__ int64_t gofs[RADIX];
-	__shared__ uint32_t ws[33];
-
-	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	const uint64_t tile_base = (uint64_t)blockIdx.x * RS_TILE;
-	const int tile_cnt = (int)min((uint64_t)RS_TILE, n - tile_base);
-
-#pragma unroll
-	for (int k = 0; k < RS_WARPS; ++k)
-		wh[k][threadIdx.x] = 0;
-
-	// global digit bases: exclusive scan of the 256 digit totals
-	const uint32_t dig_total = totals[threadIdx.x];
-	const uint32_t dig_base = block_exscan(dig_total, ws, nullptr); // contains __syncthreads
-
-	// warp-striped arrangement: warp w owns tile positions [w*32*ITEMS, (w+1)*32*ITEMS),
-	// item k of lane l sits at w*32*ITEMS + k*32 + l -> memory order == (k, l) order per warp
-	uint64_t key[RS_ITEMS];
-	uint32_t val[RS_ITEMS];
-	uint32_t rank[RS_ITEMS];
-	const int wbase = w * 32 * RS_ITEMS;
-#pragma unroll
-	for (int k = 0; k < RS_ITEMS; ++k) {
-		const int pos = wbase + k * 32 + lane;
-		const bool ok = pos < tile_cnt;
-		key[k] = ok ? keys_in[tile_base + pos] : ~0ull;
-		val[k] = ok ? vals_in[tile_base + pos] : 0u;
-	}
-	const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll
-	for (int k = 0; k < RS_ITEMS; ++k) {
-		const int pos = wbase + k * 32 + lane;
-		const bool ok = pos < tile_cnt;
-		const uint32_t d = ok ? (uint32_t)((key[k] >> shift) & 0xff) : 256u;
-		const uint32_t peers = __match_any_sync(0xffffffffu, d);
-		uint32_t before = 0;
-		if (ok)
-			before = wh[w][d];
-		__syncwarp();
-		rank[k] = before + __popc(peers & lt);
-		if (ok && lane == (__ffs(peers) - 1))
-			wh[w][d] = before + __popc(peers);
-		__syncwarp();
-	}
-	__syncthreads();
-
-	// per digit (thread == digit): exclusive scan over warps, block count
-	uint32_t run = 0;
-#pragma unroll
-	for (int k = 0; k < RS_WARPS; ++k) {
-		const uint32_t c = wh[k][threadIdx.x];
-		wh[k][threadIdx.x] = run;
-		run += c;
-	}
-	const uint32_t lb = block_exscan(run, ws, nullptr);
-	lbase[threadIdx.x] = lb;
-	gofs[threadIdx.x] = (int64_t)dig_base +
-	                    (int64_t)counts[(uint64_t)threadIdx.x * n_tiles + blockIdx.x] - (int64_t)lb;
-	__syncthreads();
-
-	// stage the tile in digit order (stable)
-#pragma unroll
-	for (int k = 0; k < RS_ITEMS; ++k) {
-		const int pos = wbase + k * 32 + lane;
-		if (pos < tile_cnt) {
-			const uint32_t d = (uint32_t)((key[k] >> shift) & 0xff);
-			const uint32_t lp = lbase[d] + wh[w][d] + rank[k];
-			s_keys[lp] = key[k];
-			s_vals[lp] = val[k];
-		}
-	}
-	__syncthreads();
-
-	// coalesced scatter: consecutive threads write consecutive addresses inside each digit run
-#pragma unroll
-	for (int k = 0; k < RS_ITEMS; ++k) {
-		const int i = k * RS_THREADS + threadIdx.x;
-		if (i < tile_cnt) {
-			const uint64_t kk = s_keys[i];
-			const uint32_t d = (uint32_t)((kk >> shift) & 0xff);
-			const int64_t g = gofs[d] + i;
-			keys_out[g] = kk;
-			vals_out[g] = s_vals[i];
-		}
-	}
-}
+// 3. sort: radix_sort_pairs() in sort.cu (one kernel per 8-bit pass, decoupled look-back)
 
 // ------------------------------------------------------------------------------------------------
 // 4. Karras hierarchy
@@ -476,15 +298,12 @@ int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 	if (n > 0x7ffffffeull)
 		return fail(c, PRT_E_LIMIT, "set_tris: more than 2^31-2 triangles");
 
-	const uint32_t n_tiles = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
 	PRT_CUDA(c, c->nodes.reserve(c->n_nodes * sizeof(Node)));
 	PRT_CUDA(c, c->trirecs.reserve((n + 1) * sizeof(TriRec)));
 	PRT_CUDA(c, c->keys[0].reserve(n * 8));
 	PRT_CUDA(c, c->keys[1].reserve(n * 8));
 	PRT_CUDA(c, c->vals[0].reserve(n * 4));
 	PRT_CUDA(c, c->vals[1].reserve(n * 4));
-	PRT_CUDA(c, c->counts.reserve((size_t)RADIX * n_tiles * 4));
-	PRT_CUDA(c, c->totals.reserve(RADIX * 4 * 8));
 	PRT_CUDA(c, c->bounds.reserve(6 * 4));
 	PRT_CUDA(c, c->leaf_box.reserve(n * 32));
 	PRT_CUDA(c, c->node_box.reserve(n * 32));
@@ -494,7 +313,6 @@ int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 
 	const int stream_grid = (int)std::min<uint64_t>((n + TT - 1) / TT, (uint64_t)c->sm_count * 8);
 	const int bits = morton_bits_for(n);
-	const int passes = (3 * bits + 7) / 8;
 
 	k_bounds_init<<<1, 32, 0, s>>>(c->bounds.as<uint32_t>());
 	k_bounds<<<stream_grid, TT, 0, s>>>(d_tris9, n, c->bounds.as<uint32_t>());
@@ -504,19 +322,10 @@ int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 
 	int cur = 0;
 	if (n > 1) {
-		PRT_CUDA(c, cudaMemsetAsync(c->totals.p, 0, RADIX * 4 * passes, s));
-		for (int p = 0; p < passes; ++p) {
-			uint32_t *tot = c->totals.as<uint32_t>() + p * RADIX;
-			k_sort_hist<<<n_tiles, RS_THREADS, 0, s>>>(c->keys[cur].as<uint64_t>(), n, 8 * p,
-			                                           c->counts.as<uint32_t>(), tot, n_tiles);
-			k_sort_scan<<<RADIX, RS_THREADS, 0, s>>>(c->counts.as<uint32_t>(), n_tiles);
-			k_sort_scatter<<<n_tiles, RS_THREADS, 0, s>>>(
-			    c->keys[cur].as<uint64_t>(), c->vals[cur].as<uint32_t>(),
-			    c->keys[cur ^ 1].as<uint64_t>(), c->vals[cur ^ 1].as<uint32_t>(), n, 8 * p,
-			    c->counts.as<uint32_t>(), tot, n_tiles);
-			c->launches += 3;
-			cur ^= 1;
-		}
+		uint64_t *const kk[2] = {c->keys[0].as<uint64_t>(), c->keys[1].as<uint64_t>()};
+		uint32_t *const vv[2] = {c->vals[0].as<uint32_t>(), c->vals[1].as<uint32_t>()};
+		if (int rc = radix_sort_pairs(c, c->sort_scratch, kk, vv, n, 3 * bits, s, &cur))
+			return rc;
 	}
 
 	const int g = (int)((n + 255) / 256);

@@ -83,11 +83,21 @@ struct prt_b200 {
 	prt::DevBuf trirecs;   // prt::TriRec[n_tris]
 
 	// build scratch
-	prt::DevBuf keys[2], vals[2], counts, totals, bounds, leaf_box, node_box, parent, leaf_parent,
+	prt::DevBuf keys[2], vals[2], sort_scratch, bounds, leaf_box, node_box, parent, leaf_parent,
 	    flags;
 
 	// trace scratch
 	prt::DevBuf rays_dev[2], hits_dev[2], counter;
+	// ray reordering scratch, one set per launch slot (the host entry point runs two streams)
+	struct RaySort {
+		prt::DevBuf keys[2], vals[2], scratch;
+	} rs[2];
+	prt::DevBuf probe_ticket;                    // 2 x u64 block tickets of the coherence probe
+	unsigned long long *probe_host = nullptr;    // 2 x u64 mapped pinned flags (host view)
+	unsigned long long *probe_dev = nullptr;     // ... and their device view
+	int sort_rays = 2; // env PRT_B200_SORT_RAYS: 0 never, 1 always, 2 auto (only incoherent batches)
+	float scene_lo[3] = {0.f, 0.f, 0.f}, scene_hi[3] = {0.f, 0.f, 0.f};
+	uint64_t sorted_batches = 0, unsorted_batches = 0;
 	prt::PinnedBuf rays_pin[2], hits_pin[2];
 
 	prt_trace_opts opts{1, 1e-4f, 64.0f};
@@ -132,6 +142,10 @@ struct TraceOut {
 };
 int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, const TraceOut &out,
                  uint32_t *d_counts, cudaStream_t stream);
+
+// sort.cu
+int radix_sort_pairs(prt_b200 *c, DevBuf &scratch, uint64_t *const keys[2], uint32_t *const vals[2],
+                     uint64_t n, int key_bits, cudaStream_t s, int *result_index);
 
 int launch_read_probe(prt_b200 *c, const void *buf, uint64_t bytes, int iters, float *ms);
 

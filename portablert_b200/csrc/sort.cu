@@ -1,0 +1,253 @@
+// sort.cu -- LSD radix sort of (u64 key, u32 value) pairs, 8-bit digits, one kernel per pass.
+//
+// Used by the LBVH build (Morton keys -> triangle order) and by the ray reordering in front of the
+// traversal.  "Onesweep" organisation: one read of the keys produces the digit histograms of ALL
+// passes; each pass is then a single kernel in which a tile (block) ranks its keys in shared
+// memory with warp-level match/prefix operations, obtains the global offset of each of its 256
+// digit runs by a decoupled look-back over the preceding tiles' published counts (one thread per
+// digit), and scatters the tile through shared memory so that consecutive threads write
+// consecutive addresses.  HBM traffic per pass: read (8+4) B + write (8+4) B per pair.
+// Tiles take their index from an atomic counter, so a tile's predecessors are always already
+// running: the look-back cannot deadlock.
+#include <algorithm>
+
+#include "prt_ctx.h"
+
+namespace prt {
+
+constexpr int SO_THREADS = 256;
+constexpr int SO_ITEMS = 12;
+constexpr int SO_TILE = SO_THREADS * SO_ITEMS; // 3072 pairs per tile
+constexpr int SO_WARPS = SO_THREADS / 32;
+constexpr int SO_RADIX = 256;
+constexpr int SO_MAX_PASSES = 8;
+
+constexpr unsigned long long ST_LOCAL = 1ull << 62;  // tile's own count is published
+constexpr unsigned long long ST_PREFIX = 2ull << 62; // inclusive prefix over tiles 0..t is published
+constexpr unsigned long long ST_MASK = (1ull << 62) - 1;
+
+// ---- all passes' digit histograms in one read of the keys ---------------------------------------
+__global__ void __launch_bounds__(SO_THREADS)
+    k_sweep_hist(const uint64_t *__restrict__ keys, uint64_t n, int passes,
+                 uint32_t *__restrict__ ghist /* [passes][256] */) {
+	__shared__ uint32_t sh[SO_MAX_PASSES][SO_RADIX];
+	for (int p = 0; p < passes; ++p)
+		sh[p][threadIdx.x] = 0;
+	__syncthreads();
+	const uint64_t stride = (uint64_t)gridDim.x * SO_THREADS;
+	for (uint64_t i = (uint64_t)blockIdx.x * SO_THREADS + threadIdx.x; i < n; i += stride) {
+		const uint64_t k = keys[i];
+		const unsigned act = __activemask();
+		for (int p = 0; p < passes; ++p) {
+			// a digit that is constant across the warp (e.g. unused high bits) would serialise
+			// 32 same-address atomics: aggregate it into one
+			const uint32_t d = (uint32_t)(k >> (8 * p)) & 0xff;
+			int same;
+			__match_all_sync(act, d, &same);
+			if (same) {
+				if ((threadIdx.x & 31) == (__ffs(act) - 1))
+					atomicAdd(&sh[p][d], (uint32_t)__popc(act));
+			} else {
+				atomicAdd(&sh[p][d], 1u);
+			}
+		}
+	}
+	__syncthreads();
+	for (int p = 0; p < passes; ++p) {
+		const uint32_t c = sh[p][threadIdx.x];
+		if (c)
+			atomicAdd(&ghist[p * SO_RADIX + threadIdx.x], c);
+	}
+}
+
+// block-wide exclusive scan of one value per thread (SO_THREADS threads)
+__device__ __forceinline__ uint32_t block_exscan256(uint32_t v, uint32_t *ws) {
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	uint32_t inc = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+		if (lane >= o)
+			inc += t;
+	}
+	if (lane == 31)
+		ws[w] = inc;
+	__syncthreads();
+	if (w == 0) {
+		const uint32_t s = lane < SO_WARPS ? ws[lane] : 0;
+		uint32_t si = s;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, si, o);
+			if (lane >= o)
+				si += t;
+		}
+		ws[lane] = si - s;
+	}
+	__syncthreads();
+	const uint32_t res = ws[w] + inc - v;
+	__syncthreads();
+	return res;
+}
+
+// histogram -> exclusive digit offsets, per pass (one block per pass)
+__global__ void __launch_bounds__(SO_THREADS) k_sweep_offsets(uint32_t *__restrict__ ghist) {
+	__shared__ uint32_t ws[32];
+	uint32_t *h = ghist + blockIdx.x * SO_RADIX;
+	const uint32_t v = h[threadIdx.x];
+	h[threadIdx.x] = block_exscan256(v, ws);
+}
+
+// ---- one pass --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SO_THREADS)
+    k_sweep_pass(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                 uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint64_t n,
+                 int shift, const uint32_t *__restrict__ digit_ofs /* [256] exclusive */,
+                 unsigned long long *status /* [n_tiles][256] */, uint32_t *tile_counter) {
+	__shared__ uint64_t s_keys[SO_TILE];
+	__shared__ uint32_t s_vals[SO_TILE];
+	__shared__ uint32_t wh[SO_WARPS][SO_RADIX];
+	__shared__ uint32_t lbase[SO_RADIX];
+	__shared__ long long gofs[SO_RADIX];
+	__shared__ uint32_t ws[32];
+	__shared__ uint32_t s_tile;
+
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	if (threadIdx.x == 0)
+		s_tile = atomicAdd(tile_counter, 1u);
+#pragma unroll
+	for (int k = 0; k < SO_WARPS; ++k)
+		wh[k][threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t tile = s_tile;
+	const uint64_t tile_base = (uint64_t)tile * SO_TILE;
+	const int tile_cnt = (int)min((uint64_t)SO_TILE, n - tile_base);
+
+	// warp-striped arrangement: warp w owns tile positions [w*32*ITEMS, (w+1)*32*ITEMS); item k of
+	// lane l sits at w*32*ITEMS + k*32 + l, so memory order == (k, lane) order inside a warp
+	uint64_t key[SO_ITEMS];
+	uint32_t val[SO_ITEMS];
+	uint32_t rank[SO_ITEMS];
+	const int wbase = w * 32 * SO_ITEMS;
+#pragma unroll
+	for (int k = 0; k < SO_ITEMS; ++k) {
+		const int pos = wbase + k * 32 + lane;
+		const bool ok = pos < tile_cnt;
+		key[k] = ok ? keys_in[tile_base + pos] : ~0ull;
+		val[k] = ok ? vals_in[tile_base + pos] : 0u;
+	}
+	const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+	for (int k = 0; k < SO_ITEMS; ++k) {
+		const int pos = wbase + k * 32 + lane;
+		const bool ok = pos < tile_cnt;
+		const uint32_t d = ok ? (uint32_t)((key[k] >> shift) & 0xff) : 256u;
+		const uint32_t peers = __match_any_sync(0xffffffffu, d);
+		uint32_t before = 0;
+		if (ok)
+			before = wh[w][d];
+		__syncwarp();
+		rank[k] = before + __popc(peers & lt);
+		if (ok && lane == (__ffs(peers) - 1))
+			wh[w][d] = before + __popc(peers);
+		__syncwarp();
+	}
+	__syncthreads();
+
+	// per digit (thread == digit): exclusive scan over the warps, tile count
+	uint32_t cnt = 0;
+#pragma unroll
+	for (int k = 0; k < SO_WARPS; ++k) {
+		const uint32_t c = wh[k][threadIdx.x];
+		wh[k][threadIdx.x] = cnt;
+		cnt += c;
+	}
+	// publish this tile's count, then look back for the sum over the preceding tiles
+	unsigned long long *my = status + (uint64_t)tile * SO_RADIX + threadIdx.x;
+	if (tile == 0) {
+		__stcg(my, ST_PREFIX | cnt);
+	} else {
+		__stcg(my, ST_LOCAL | cnt);
+	}
+	unsigned long long prefix = 0;
+	if (tile > 0) {
+		long long t = (long long)tile - 1;
+		while (true) {
+			const unsigned long long v = __ldcg(status + (uint64_t)t * SO_RADIX + threadIdx.x);
+			if ((v >> 62) == 0) {
+				__nanosleep(20);
+				continue;
+			}
+			prefix += v & ST_MASK;
+			if ((v >> 62) == 2 || t == 0)
+				break;
+			--t;
+		}
+		__stcg(my, ST_PREFIX | (prefix + cnt));
+	}
+	const uint32_t lb = block_exscan256(cnt, ws);
+	lbase[threadIdx.x] = lb;
+	gofs[threadIdx.x] = (long long)digit_ofs[threadIdx.x] + (long long)prefix - (long long)lb;
+	__syncthreads();
+
+	// stage the tile in digit order (stable), then write runs of consecutive addresses
+#pragma unroll
+	for (int k = 0; k < SO_ITEMS; ++k) {
+		const int pos = wbase + k * 32 + lane;
+		if (pos < tile_cnt) {
+			const uint32_t d = (uint32_t)((key[k] >> shift) & 0xff);
+			const uint32_t lp = lbase[d] + wh[w][d] + rank[k];
+			s_keys[lp] = key[k];
+			s_vals[lp] = val[k];
+		}
+	}
+	__syncthreads();
+#pragma unroll
+	for (int k = 0; k < SO_ITEMS; ++k) {
+		const int i = k * SO_THREADS + threadIdx.x;
+		if (i < tile_cnt) {
+			const uint64_t kk = s_keys[i];
+			const uint32_t d = (uint32_t)((kk >> shift) & 0xff);
+			const long long g = gofs[d] + i;
+			keys_out[g] = kk;
+			vals_out[g] = s_vals[i];
+		}
+	}
+}
+
+// Sorts n pairs by the low `key_bits` bits of the key (stable).  keys[0]/vals[0] hold the input;
+// the two buffers ping-pong; returns the index (0/1) of the buffer that holds the result.
+int radix_sort_pairs(prt_b200 *c, DevBuf &scratch, uint64_t *const keys[2], uint32_t *const vals[2],
+                     uint64_t n, int key_bits, cudaStream_t s, int *result_index) {
+	*result_index = 0;
+	if (n <= 1 || key_bits <= 0)
+		return PRT_OK;
+	const int passes = std::min(SO_MAX_PASSES, (key_bits + 7) / 8);
+	const uint64_t n_tiles = (n + SO_TILE - 1) / SO_TILE;
+	const size_t hist_b = (size_t)SO_MAX_PASSES * SO_RADIX * 4, ctr_b = 64;
+	const size_t status_b = (size_t)passes * n_tiles * SO_RADIX * 8;
+	PRT_CUDA(c, scratch.reserve(hist_b + ctr_b + status_b));
+	char *base = scratch.as<char>();
+	uint32_t *ghist = reinterpret_cast<uint32_t *>(base);
+	uint32_t *ctr = reinterpret_cast<uint32_t *>(base + hist_b);
+	unsigned long long *status = reinterpret_cast<unsigned long long *>(base + hist_b + ctr_b);
+	PRT_CUDA(c, cudaMemsetAsync(base, 0, hist_b + ctr_b + status_b, s));
+	const int hgrid = (int)std::min<uint64_t>((n + SO_THREADS * 8 - 1) / (SO_THREADS * 8),
+	                                          (uint64_t)c->sm_count * 8);
+	k_sweep_hist<<<hgrid, SO_THREADS, 0, s>>>(keys[0], n, passes, ghist);
+	k_sweep_offsets<<<passes, SO_THREADS, 0, s>>>(ghist);
+	c->launches += 2;
+	int cur = 0;
+	for (int p = 0; p < passes; ++p) {
+		k_sweep_pass<<<(unsigned)n_tiles, SO_THREADS, 0, s>>>(
+		    keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, 8 * p, ghist + p * SO_RADIX,
+		    status + (size_t)p * n_tiles * SO_RADIX, ctr + p);
+		c->launches += 1;
+		cur ^= 1;
+	}
+	PRT_CUDA(c, cudaGetLastError());
+	*result_index = cur;
+	return PRT_OK;
+}
+
+} // namespace prt

@@ -12,6 +12,8 @@
 // One kernel per tag mask (31, like the 31 OptiX raygen programs of hitreg.hpp:142-177) x {SoA,
 // AoS} output; only the requested fields are tracked and written.  Warps are persistent and pull
 // 32-ray packets from a global counter.
+#include <algorithm>
+
 #include "prt_ctx.h"
 #include "prt_traverse.cuh"
 
@@ -41,7 +43,88 @@ struct TraceParams {
 	float scene_absmax[3];
 	int fast; // 1: conservative FFMA test for internal culling where the ray qualifies
 	int refill; // re-fetch rays when fewer than this many lanes of a warp are still traversing
+	const uint32_t *perm; // ray processing order (reordered batches) or nullptr = identity
 };
+
+// ------------------------------------------------------------------------------------------------
+// Ray reordering.  Incoherent batches (bounce rays, random rays) make the 32 lanes of a warp walk
+// unrelated parts of the tree: every node fetch touches 32 different lines and lanes finish at
+// very different times.  Sorting the batch by a 24-bit key -- Morton code of the origin (4 bits per
+// axis inside the scene box) above the Morton code of the direction (4 bits per axis) -- puts rays
+// that start in the same region and point the same way next to each other.  The traversal then
+// processes rays in key order through a permutation; results are written to the rays' own slots,
+// so the output order is unchanged.  Measured x1.39 (10 M tris / random rays) and x1.45 (one-bounce
+// diffuse rays in the 262 k-tri interior); coherent primary rays gain nothing, which the key
+// kernel detects (most neighbouring rays already share their key) so that the sort is skipped.
+__device__ __forceinline__ uint32_t spread4(uint32_t v) { // 4 bits -> every third bit
+	return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6);
+}
+
+__device__ __forceinline__ uint32_t ray_key(const float *__restrict__ r, float3 lo, float3 inv_ext) {
+	const float ox = __ldg(r), oy = __ldg(r + 1), oz = __ldg(r + 2);
+	const float dx = __ldg(r + 3), dy = __ldg(r + 4), dz = __ldg(r + 5);
+	const float inv = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-37f));
+	// NaN / out-of-box values clamp into the grid; the key only steers the processing order
+	const uint32_t qx = (uint32_t)fminf(fmaxf((ox - lo.x) * inv_ext.x * 16.f, 0.f), 15.f);
+	const uint32_t qy = (uint32_t)fminf(fmaxf((oy - lo.y) * inv_ext.y * 16.f, 0.f), 15.f);
+	const uint32_t qz = (uint32_t)fminf(fmaxf((oz - lo.z) * inv_ext.z * 16.f, 0.f), 15.f);
+	const uint32_t ux = (uint32_t)fminf(fmaxf((dx * inv * 0.5f + 0.5f) * 16.f, 0.f), 15.f);
+	const uint32_t uy = (uint32_t)fminf(fmaxf((dy * inv * 0.5f + 0.5f) * 16.f, 0.f), 15.f);
+	const uint32_t uz = (uint32_t)fminf(fmaxf((dz * inv * 0.5f + 0.5f) * 16.f, 0.f), 15.f);
+	const uint32_t mo = (spread4(qx) << 2) | (spread4(qy) << 1) | spread4(qz);
+	const uint32_t md = (spread4(ux) << 2) | (spread4(uy) << 1) | spread4(uz);
+	return (mo << 12) | md;
+}
+
+__global__ void __launch_bounds__(256)
+    k_ray_keys(const float *__restrict__ rays, uint64_t n, float3 lo, float3 inv_ext,
+               uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) {
+		keys[i] = ray_key(rays + i * 6, lo, inv_ext);
+		vals[i] = (uint32_t)i;
+	}
+}
+
+// Coherence probe: PROBE_WARPS segments of 32 consecutive rays spread over the batch; counts the
+// rays that carry the same key as their predecessor.  The last block to finish publishes the total
+// through mapped pinned memory, so the host needs one stream synchronisation and no copy.
+constexpr int PROBE_BLOCKS = 32, PROBE_WARPS = PROBE_BLOCKS * 8;
+__global__ void __launch_bounds__(256)
+    k_ray_probe(const float *__restrict__ rays, uint64_t n, float3 lo, float3 inv_ext,
+                unsigned long long *__restrict__ acc /* same count */,
+                unsigned long long *__restrict__ ticket, volatile unsigned long long *host_flag) {
+	const int lane = threadIdx.x & 31;
+	const uint64_t warp = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+	const uint64_t n_seg = n / 32;
+	const uint64_t seg = n_seg >= PROBE_WARPS ? warp * (n_seg / PROBE_WARPS) : warp;
+	const uint64_t i = seg * 32 + lane;
+	uint32_t key = 0xffffffffu - lane; // distinct for lanes past the end
+	if (seg < n_seg)
+		key = ray_key(rays + i * 6, lo, inv_ext);
+	const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+	const unsigned m = __ballot_sync(0xffffffffu, lane != 0 && prev == key && seg < n_seg);
+	if (lane == 0 && m)
+		atomicAdd(acc, (unsigned long long)__popc(m));
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		if (atomicAdd(ticket, 1ull) == PROBE_BLOCKS - 1) {
+			*host_flag = atomicAdd(acc, 0ull) + 1; // +1: 0 means "not written yet"
+			__threadfence_system();
+		}
+	}
+}
+
+static void k_ray_probe_launch(prt_b200 *c, const float *rays, uint64_t n, float3 lo, float3 ie,
+                               unsigned long long *acc, unsigned long long *ticket,
+                               unsigned long long *host_flag_dev, cudaStream_t s) {
+	k_ray_probe<<<PROBE_BLOCKS, 256, 0, s>>>(rays, n, lo, ie, acc, ticket, host_flag_dev);
+	c->launches += 1;
+}
+
+constexpr int RAY_KEY_BITS = 24;
+constexpr uint64_t SORT_MIN_RAYS = 1u << 16;
 
 // Writes one finished ray (epilogue of bvh.hpp:259-263).
 template <uint32_t MASK, bool AOS, bool COUNT>
@@ -130,8 +213,10 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceParams P) {
 			if (base + n >= P.n_rays)
 				exhausted = true;
 			if (!has_ray) {
-				const uint64_t i = base + __popc(idle & lt);
+				uint64_t i = base + __popc(idle & lt);
 				if (i < P.n_rays) {
+					if (P.perm)
+						i = __ldg(P.perm + i);
 					float r6[6];
 #pragma unroll
 					for (int k = 0; k < 6; ++k)
@@ -222,7 +307,53 @@ int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, c
 	P.refill = c->refill;
 	PRT_CUDA(c, c->counter.reserve(256));
 	P.counter = c->counter.as<unsigned long long>() + 2 * out.slot; // 16 bytes apart
-	PRT_CUDA(c, cudaMemsetAsync(P.counter, 0, 8, s));
+	PRT_CUDA(c, cudaMemsetAsync(P.counter, 0, 16, s));               // ray counter + coherence probe
+
+	// ---- optional ray reordering (see k_ray_keys)
+	P.perm = nullptr;
+	if (c->sort_rays && !d_counts && n >= SORT_MIN_RAYS && n < (1ull << 32) && c->n_tris > 1) {
+		auto &rs = c->rs[out.slot];
+		for (int k = 0; k < 2; ++k) {
+			PRT_CUDA(c, rs.keys[k].reserve(n * 8));
+			PRT_CUDA(c, rs.vals[k].reserve(n * 4));
+		}
+		float3 lo = make_float3(c->scene_lo[0], c->scene_lo[1], c->scene_lo[2]);
+		float3 ie;
+		ie.x = c->scene_hi[0] > c->scene_lo[0] ? 1.f / (c->scene_hi[0] - c->scene_lo[0]) : 0.f;
+		ie.y = c->scene_hi[1] > c->scene_lo[1] ? 1.f / (c->scene_hi[1] - c->scene_lo[1]) : 0.f;
+		ie.z = c->scene_hi[2] > c->scene_lo[2] ? 1.f / (c->scene_hi[2] - c->scene_lo[2]) : 0.f;
+		bool do_sort = true;
+		if (c->sort_rays == 2) { // auto: skip batches that are already coherent
+			volatile unsigned long long *flag = c->probe_host + out.slot;
+			*flag = 0;
+			PRT_CUDA(c, cudaMemsetAsync(P.counter + 1, 0, 8, s));
+			PRT_CUDA(c, cudaMemsetAsync(c->probe_ticket.as<unsigned long long>() + out.slot, 0, 8, s));
+			// acc[0] = same count lives next to the ray counter, acc[1] = the block ticket
+			k_ray_probe_launch(c, d_rays6, n, lo, ie, P.counter + 1,
+			                   c->probe_ticket.as<unsigned long long>() + out.slot,
+			                   c->probe_dev + out.slot, s);
+			PRT_CUDA(c, cudaStreamSynchronize(s));
+			const unsigned long long same = *flag ? *flag - 1 : 0;
+			const uint64_t pairs = (uint64_t)std::min<uint64_t>(PROBE_WARPS, n / 32) * 31;
+			do_sort = same * 2 < pairs;
+		}
+		if (do_sort) {
+			k_ray_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+			    d_rays6, n, lo, ie, rs.keys[0].as<uint64_t>(), rs.vals[0].as<uint32_t>());
+			c->launches += 1;
+		}
+		if (do_sort) {
+			uint64_t *const kk[2] = {rs.keys[0].as<uint64_t>(), rs.keys[1].as<uint64_t>()};
+			uint32_t *const vv[2] = {rs.vals[0].as<uint32_t>(), rs.vals[1].as<uint32_t>()};
+			int cur = 0;
+			if (int rc = radix_sort_pairs(c, rs.scratch, kk, vv, n, RAY_KEY_BITS, s, &cur))
+				return rc;
+			P.perm = vv[cur];
+			c->sorted_batches++;
+		} else {
+			c->unsorted_batches++;
+		}
+	}
 
 	const bool aos = out.aos != nullptr;
 	KernelFn fn = d_counts ? (KernelFn)k_trace<PRT_TAG_ALL, false, true> : g_table[mask][aos];
