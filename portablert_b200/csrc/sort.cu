@@ -136,24 +136,15 @@ __global__ void __launch_bounds__(SO_THREADS)
 		key[k] = ok ? keys_in[tile_base + pos] : ~0ull;
 		val[k] = ok ? vals_in[tile_base + pos] : 0u;
 	}
-	const uint32_t lt = (1u << lane) - 1u;
+	// ---- early counts: warp-private digit histograms, so that the tile's counts can be published
+	// (and the successors' look-back can proceed) before the slower ranking below
 #pragma unroll
 	for (int k = 0; k < SO_ITEMS; ++k) {
 		const int pos = wbase + k * 32 + lane;
-		const bool ok = pos < tile_cnt;
-		const uint32_t d = ok ? (uint32_t)((key[k] >> shift) & 0xff) : 256u;
-		const uint32_t peers = __match_any_sync(0xffffffffu, d);
-		uint32_t before = 0;
-		if (ok)
-			before = wh[w][d];
-		__syncwarp();
-		rank[k] = before + __popc(peers & lt);
-		if (ok && lane == (__ffs(peers) - 1))
-			wh[w][d] = before + __popc(peers);
-		__syncwarp();
+		if (pos < tile_cnt)
+			atomicAdd(&wh[w][(uint32_t)(key[k] >> shift) & 0xff], 1u);
 	}
 	__syncthreads();
-
 	// per digit (thread == digit): exclusive scan over the warps, tile count
 	uint32_t cnt = 0;
 #pragma unroll
@@ -162,22 +153,44 @@ __global__ void __launch_bounds__(SO_THREADS)
 		wh[k][threadIdx.x] = cnt;
 		cnt += c;
 	}
-	// publish this tile's count, then look back for the sum over the preceding tiles
 	unsigned long long *my = status + (uint64_t)tile * SO_RADIX + threadIdx.x;
-	if (tile == 0) {
-		__stcg(my, ST_PREFIX | cnt);
-	} else {
-		__stcg(my, ST_LOCAL | cnt);
+	__stcg(my, (tile == 0 ? ST_PREFIX : ST_LOCAL) | cnt);
+	__syncthreads();
+
+	// ---- ranking: position of every key among the keys of its digit inside the tile (stable).
+	// Peers (lanes holding the same digit in this round) are found with 8 ballots -- MATCH.ANY
+	// costs one iteration per distinct value, ~30 for random digits.
+	const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+	for (int k = 0; k < SO_ITEMS; ++k) {
+		const int pos = wbase + k * 32 + lane;
+		const bool ok = pos < tile_cnt;
+		const uint32_t d = (uint32_t)(key[k] >> shift) & 0xff;
+		uint32_t peers = __ballot_sync(0xffffffffu, ok);
+#pragma unroll
+		for (int bit = 0; bit < 8; ++bit) {
+			const bool one = (d >> bit) & 1u;
+			const uint32_t bal = __ballot_sync(0xffffffffu, one);
+			peers &= one ? bal : ~bal;
+		}
+		uint32_t before = 0;
+		if (ok)
+			before = wh[w][d]; // running offset of this digit inside the warp's part of the tile
+		__syncwarp();
+		rank[k] = before + __popc(peers & lt);
+		if (ok && lane == (__ffs(peers) - 1))
+			wh[w][d] = before + __popc(peers);
+		__syncwarp();
 	}
+
+	// ---- decoupled look-back: sum of this digit's counts over the preceding tiles
 	unsigned long long prefix = 0;
 	if (tile > 0) {
 		long long t = (long long)tile - 1;
 		while (true) {
 			const unsigned long long v = __ldcg(status + (uint64_t)t * SO_RADIX + threadIdx.x);
-			if ((v >> 62) == 0) {
-				__nanosleep(20);
+			if ((v >> 62) == 0)
 				continue;
-			}
 			prefix += v & ST_MASK;
 			if ((v >> 62) == 2 || t == 0)
 				break;
@@ -196,7 +209,7 @@ __global__ void __launch_bounds__(SO_THREADS)
 		const int pos = wbase + k * 32 + lane;
 		if (pos < tile_cnt) {
 			const uint32_t d = (uint32_t)((key[k] >> shift) & 0xff);
-			const uint32_t lp = lbase[d] + wh[w][d] + rank[k];
+			const uint32_t lp = lbase[d] + rank[k];
 			s_keys[lp] = key[k];
 			s_vals[lp] = val[k];
 		}
