@@ -108,6 +108,10 @@ int prt_b200_nearest_hits(prt_b200 *ctx, const float *rays6, uint64_t n_rays, ui
  * std::vector, as in the reference API) is staged through internal pinned buffers. */
 void *prt_b200_alloc_pinned(size_t bytes);
 void prt_b200_free_pinned(void *p);
+/* Page-lock / unlock an existing host range (cudaHostRegister), e.g. this process' slice of a
+ * shared-memory segment holding the whole ray batch of a multi-GPU job. */
+int prt_b200_host_register(void *p, size_t bytes);
+int prt_b200_host_unregister(void *p);
 
 /* Device-resident traversal for device-timed measurement: rays and outputs live on the context's
  * device.  *trace_ms (may be NULL) = device time of the traversal kernel(s), CUDA events on the

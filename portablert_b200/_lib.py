@@ -58,6 +58,8 @@ SYMBOLS = {
     "prt_b200_read_bandwidth": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
     "prt_b200_alloc_pinned": (C.c_void_p, [C.c_size_t]),
     "prt_b200_free_pinned": (None, [C.c_void_p]),
+    "prt_b200_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "prt_b200_host_unregister": (C.c_int, [C.c_void_p]),
     "prt_b200_last_error": (C.c_char_p, [C.c_void_p]),
 }
 

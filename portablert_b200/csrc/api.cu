@@ -424,6 +424,21 @@ void prt_b200_free_pinned(void *p) {
 	if (p)
 		cudaFreeHost(p);
 }
+// Page-lock an existing host range (e.g. a slice of a shared-memory segment that several
+// single-GPU processes use as their common ray / hit buffers) so that the host entry points DMA
+// directly.  Returns 0 on success.
+int prt_b200_host_register(void *p, size_t bytes) {
+	const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+	if (e != cudaSuccess)
+		cudaGetLastError();
+	return e == cudaSuccess ? PRT_OK : PRT_E_CUDA;
+}
+int prt_b200_host_unregister(void *p) {
+	const cudaError_t e = cudaHostUnregister(p);
+	if (e != cudaSuccess)
+		cudaGetLastError();
+	return e == cudaSuccess ? PRT_OK : PRT_E_CUDA;
+}
 
 // Bandwidth probe: a persistent grid repeatedly reads `bytes` of device memory with 16-byte
 // loads.  With bytes << L2 (126 MB) it measures L2 read bandwidth, with bytes >> L2 HBM read

@@ -118,6 +118,58 @@ def gather_hits(local_hits: np.ndarray, R: int, device, dst: int = 0, group=None
     return out.cpu().numpy().reshape(-1).view(local_hits.dtype).copy()
 
 
+class SharedHostBatch:
+    """Single-node fast path for host-resident batches: the ray batch and the hit records live in
+    one POSIX shared-memory segment each (/dev/shm); every rank page-locks ITS OWN contiguous slice
+    and lets the host entry point DMA it straight to/from its GPU.  All PCIe links work in parallel
+    and the hits land in ray order in the shared result -- no funnel through rank 0, no collective
+    on the data path.  (The NCCL scatter/gather above is for batches that live on a GPU.)"""
+
+    def __init__(self, name: str, n_rays: int, hit_dtype, rank: int, world: int, create: bool):
+        import ctypes as C
+
+        from ._lib import lib
+        self.n, self.rank, self.world = n_rays, rank, world
+        self.paths = (f"/dev/shm/{name}_rays", f"/dev/shm/{name}_hits")
+        mode = "w+" if create else "r+"
+        self.rays = np.memmap(self.paths[0], np.float32, mode, shape=(n_rays, 6))
+        self.hits = np.memmap(self.paths[1], np.dtype(hit_dtype), mode, shape=(n_rays,))
+        self.lo, self.hi = slice_bounds(n_rays, world, rank)
+        self._reg = []
+        page = 4096
+        for arr, item in ((self.rays, 24), (self.hits, np.dtype(hit_dtype).itemsize)):
+            base = arr.ctypes.data
+            a = (base + self.lo * item) // page * page
+            b = -(-(base + self.hi * item) // page) * page
+            end = -(-(base + n_rays * item) // page) * page
+            b = min(b, end)
+            if b > a and lib().prt_b200_host_register(C.c_void_p(a), b - a) == 0:
+                self._reg.append(a)
+
+    @property
+    def my_rays(self):
+        return self.rays[self.lo:self.hi]
+
+    @property
+    def my_hits(self):
+        return self.hits[self.lo:self.hi]
+
+    def close(self, unlink: bool):
+        import ctypes as C
+        import os
+
+        from ._lib import lib
+        for a in self._reg:
+            lib().prt_b200_host_unregister(C.c_void_p(a))
+        self._reg = []
+        if unlink:
+            for p in self.paths:
+                try:
+                    os.unlink(p)
+                except OSError:
+                    pass
+
+
 def sharded_nearest_hits(set_tris, trace, tris, rays, device, src: int = 0, group=None):
     """The whole multi-GPU call: `set_tris(tris_np)` and `trace(rays_np) -> structured hits` are the
     per-rank backend calls (CUDABackend.set_tris / .nearest_hits bound to this rank's GPU); `tris`
