@@ -143,6 +143,7 @@ int prt_b200_trace_count_dev(prt_b200 *ctx, const float *d_rays6, uint64_t n_ray
 /* Introspection for tests and the bench. */
 uint64_t prt_b200_num_tris(const prt_b200 *ctx);
 uint64_t prt_b200_num_nodes(const prt_b200 *ctx);
+int32_t prt_b200_bvh_root(const prt_b200 *ctx);       /* index of the root node in the node array */
 uint64_t prt_b200_bvh_bytes(const prt_b200 *ctx);      /* node array + triangle array on device */
 uint64_t prt_b200_launch_count(const prt_b200 *ctx);   /* kernels launched by this context so far */
 float prt_b200_last_build_ms(const prt_b200 *ctx);     /* device time of the last build */

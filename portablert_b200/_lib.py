@@ -50,6 +50,7 @@ SYMBOLS = {
     "prt_b200_trace_count_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "prt_b200_num_tris": (C.c_uint64, [C.c_void_p]),
     "prt_b200_num_nodes": (C.c_uint64, [C.c_void_p]),
+    "prt_b200_bvh_root": (C.c_int32, [C.c_void_p]),
     "prt_b200_bvh_bytes": (C.c_uint64, [C.c_void_p]),
     "prt_b200_launch_count": (C.c_uint64, [C.c_void_p]),
     "prt_b200_last_build_ms": (C.c_float, [C.c_void_p]),

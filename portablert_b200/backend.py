@@ -179,6 +179,10 @@ class CUDABackend(Backend):
         return lib().prt_b200_num_nodes(self._h)
 
     @property
+    def bvh_root(self):
+        return lib().prt_b200_bvh_root(self._h)
+
+    @property
     def bvh_bytes(self):
         return lib().prt_b200_bvh_bytes(self._h)
 

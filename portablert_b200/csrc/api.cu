@@ -118,7 +118,7 @@ void prt_b200_destroy(prt_b200 *c) {
 		cudaStreamSynchronize(c->stream);
 	prt::DevBuf *bufs[] = {&c->tris_raw, &c->nodes,    &c->trirecs,     &c->keys[0],     &c->keys[1],
 	                       &c->vals[0],  &c->vals[1],  &c->sort_scratch, &c->bounds,
-	                       &c->leaf_box, &c->node_box, &c->parent,      &c->leaf_parent, &c->flags,
+	                       &c->leaf_box, &c->bound,    &c->root_info,
 	                       &c->rays_dev[0], &c->rays_dev[1], &c->hits_dev[0], &c->hits_dev[1],
 	                       &c->counter};
 	for (auto *b : bufs)
@@ -184,21 +184,21 @@ static int timed_build(prt_b200 *c, const float *d_tris9, uint64_t n, float *ms)
 	if (rc)
 		return rc;
 	PRT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
-	// scene bounds for the fast box test's error margin: the root node carries both halves
-	prt::Node root;
+	// root index + scene box (fast box test margin, ray-sort grid), published by the build
+	struct {
+		int32_t root;
+		float lo[3], hi[3];
+		int32_t pad;
+	} ri{};
 	if (c->n_nodes)
-		PRT_CUDA(c, cudaMemcpyAsync(&root, c->nodes.p, sizeof root, cudaMemcpyDeviceToHost, c->stream));
+		PRT_CUDA(c, cudaMemcpyAsync(&ri, c->root_info.p, sizeof ri, cudaMemcpyDeviceToHost, c->stream));
 	PRT_CUDA(c, cudaStreamSynchronize(c->stream));
 	PRT_CUDA(c, cudaEventElapsedTime(&c->last_build_ms, c->ev0, c->ev1));
+	c->root = c->n_nodes ? ri.root : 0;
 	for (int a = 0; a < 3; ++a) {
-		float m = 0.f;
-		if (c->n_nodes) {
-			m = std::max(std::fabs(root.lo0[a]), std::fabs(root.hi0[a]));
-			m = std::max(m, std::max(std::fabs(root.lo1[a]), std::fabs(root.hi1[a])));
-		}
-		c->scene_absmax[a] = m;
-		c->scene_lo[a] = c->n_nodes ? std::min(root.lo0[a], root.lo1[a]) : 0.f;
-		c->scene_hi[a] = c->n_nodes ? std::max(root.hi0[a], root.hi1[a]) : 0.f;
+		c->scene_lo[a] = c->n_nodes ? ri.lo[a] : 0.f;
+		c->scene_hi[a] = c->n_nodes ? ri.hi[a] : 0.f;
+		c->scene_absmax[a] = std::max(std::fabs(c->scene_lo[a]), std::fabs(c->scene_hi[a]));
 	}
 	if (ms)
 		*ms = c->last_build_ms;
@@ -463,6 +463,7 @@ int prt_b200_read_bandwidth(prt_b200 *c, uint64_t bytes, int iters, float *gbs) 
 
 uint64_t prt_b200_num_tris(const prt_b200 *c) { return c ? c->n_tris : 0; }
 uint64_t prt_b200_num_nodes(const prt_b200 *c) { return c ? c->n_nodes : 0; }
+int32_t prt_b200_bvh_root(const prt_b200 *c) { return c ? c->root : 0; }
 uint64_t prt_b200_bvh_bytes(const prt_b200 *c) {
 	return c ? c->n_nodes * sizeof(prt::Node) + c->n_tris * sizeof(prt::TriRec) : 0;
 }

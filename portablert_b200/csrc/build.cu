@@ -7,10 +7,10 @@
 //   3 sort      LSD radix sort (sort.cu): 8-bit digits, (u64 key, u32 index), one kernel per pass,
 //               tiles ranked in shared memory with warp-level match/prefix operations,
 //               decoupled look-back for the global offsets, coalesced scatter
-//   4 karras    one thread per internal node: range + split (Karras 2012), parent links
-//   5 leaves    gather triangles into Morton order as 64-byte records (v0, edges, own AABB)
-//   6 refit     bottom-up, second-arriver-continues with one atomic counter per node; writes the
-//               final 64-byte nodes that carry both children's exact boxes
+//   4 hierarchy one bottom-up kernel: gather triangles into Morton order as 64-byte records (v0,
+//               edges, own AABB), find each subtree's parent from the neighbouring key deltas
+//               (the Karras 2012 radix tree, built bottom-up as in Apetrei 2014), write the final
+//               64-byte nodes that carry both children's exact boxes; one atomicExch per node
 // HBM-bound integer/byte work: no tensor cores.  Algorithmic bytes per triangle are tallied in
 // DESIGN.md (build roofline).
 #include <algorithm>
@@ -156,28 +156,103 @@ __global__ void __launch_bounds__(TT) k_morton(const float *__restrict__ tris9, 
 // 3. sort: radix_sort_pairs() in sort.cu (one kernel per 8-bit pass, decoupled look-back)
 
 // ------------------------------------------------------------------------------------------------
-// 4. Karras hierarchy
+// 4. hierarchy + triangle records + boxes in ONE bottom-up pass
 // ------------------------------------------------------------------------------------------------
+// delta(i) = "distance" between the sorted (key . index) pairs i and i+1; a smaller value means a
+// longer common prefix.  Indices break ties between equal Morton keys, so the pairs are distinct and
+// the two candidate deltas of a range never tie.
+__device__ __forceinline__ bool delta_less(const uint64_t *__restrict__ keys, int a, int b) {
+	const uint64_t xa = __ldg(keys + a) ^ __ldg(keys + a + 1);
+	const uint64_t xb = __ldg(keys + b) ^ __ldg(keys + b + 1);
+	if (xa != xb)
+		return xa < xb;
+	return (uint32_t)(a ^ (a + 1)) < (uint32_t)(b ^ (b + 1));
+}
+
+struct RootInfo {
+	int32_t root;
+	float lo[3], hi[3];
+	int32_t pad;
+};
+
+// One thread per triangle (in Morton order).  It gathers its triangle, writes the 64-byte record
+// and then climbs: a subtree covering the sorted range [l, r] hangs under internal node r (as its
+// left child) if delta(r) < delta(l-1), else under node l-1 (as its right child) -- the binary
+// radix tree of Karras 2012 found bottom-up (Apetrei 2014), so no separate top-down hierarchy pass
+// and no parent pointers are needed.  The climbing thread writes ITS half of the parent's node
+// (child reference + the child's exact box), then swaps its range bound into bound[p]: the first
+// arrival finds -1 and retires, the second finds its sibling's bound, reads the sibling's box from
+// the node, and carries the union upwards.  Which thread arrives first does not influence what
+// is written, so the build is deterministic.
 __global__ void __launch_bounds__(256)
-    k_karras(const uint64_t *__restrict__ keys, int64_t n, Node *__restrict__ nodes,
-             int32_t *__restrict__ parent, int32_t *__restrict__ leaf_parent) {
-	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n - 1)
+    k_hierarchy(const float *__restrict__ tris9, const uint32_t *__restrict__ sorted_idx,
+                const uint64_t *__restrict__ keys, int n, TriRec *__restrict__ recs, Node *nodes,
+                int *bound, RootInfo *root_info) {
+	const int j = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+	if (j >= n)
 		return;
-	int32_t l, r;
-	karras_node(keys, n, i, l, r);
-	nodes[i].child0 = l;
-	nodes[i].child1 = r;
-	if (l < 0)
-		leaf_parent[~l] = (int32_t)i;
-	else
-		parent[l] = (int32_t)i;
-	if (r < 0)
-		leaf_parent[~r] = (int32_t)i;
-	else
-		parent[r] = (int32_t)i;
-	if (i == 0)
-		parent[0] = -1;
+	const uint32_t prim = sorted_idx[j];
+	const float *src = tris9 + (uint64_t)prim * 9;
+	float t[9];
+#pragma unroll
+	for (int k = 0; k < 9; ++k)
+		t[k] = __ldg(src + k);
+	Box b = tri_box(t);
+	float4 *rec = reinterpret_cast<float4 *>(recs + j);
+	// edges exactly as core.hpp:33-35 computes them
+	rec[0] = make_float4(t[0], t[1], t[2], __uint_as_float(prim));
+	rec[1] = make_float4(fsub(t[3], t[0]), fsub(t[4], t[1]), fsub(t[5], t[2]), b.lo[0]);
+	rec[2] = make_float4(fsub(t[6], t[0]), fsub(t[7], t[1]), fsub(t[8], t[2]), b.lo[1]);
+	rec[3] = make_float4(b.lo[2], b.hi[0], b.hi[1], b.hi[2]);
+
+	int l = j, r = j;
+	int32_t ref = ~j;
+	for (;;) {
+		const bool left_child = (l == 0) || (r != n - 1 && delta_less(keys, r, l - 1));
+		const int p = left_child ? r : l - 1;
+		float2 *nd = reinterpret_cast<float2 *>(nodes + p);
+		int32_t *ni = reinterpret_cast<int32_t *>(nodes + p);
+		if (left_child) { // floats 0..5 = child0 box, int 12 = child0
+			nd[0] = make_float2(b.lo[0], b.lo[1]);
+			nd[1] = make_float2(b.lo[2], b.hi[0]);
+			nd[2] = make_float2(b.hi[1], b.hi[2]);
+			ni[12] = ref;
+		} else { // floats 6..11 = child1 box, int 13 = child1
+			nd[3] = make_float2(b.lo[0], b.lo[1]);
+			nd[4] = make_float2(b.lo[2], b.hi[0]);
+			nd[5] = make_float2(b.hi[1], b.hi[2]);
+			ni[13] = ref;
+		}
+		__threadfence();
+		const int other = atomicExch(&bound[p], left_child ? l : r);
+		if (other == -1)
+			return; // first arrival: the sibling will carry on
+		__threadfence();
+		const float2 *sib = reinterpret_cast<const float2 *>(nodes + p) + (left_child ? 3 : 0);
+		const float2 s0 = __ldcg(sib), s1 = __ldcg(sib + 1), s2 = __ldcg(sib + 2);
+		Box o;
+		o.lo[0] = s0.x;
+		o.lo[1] = s0.y;
+		o.lo[2] = s1.x;
+		o.hi[0] = s1.y;
+		o.hi[1] = s2.x;
+		o.hi[2] = s2.y;
+		b = box_union(b, o);
+		if (left_child)
+			r = other;
+		else
+			l = other;
+		ref = p;
+		if (l == 0 && r == n - 1) { // the root: publish its index and the scene box
+			root_info->root = p;
+#pragma unroll
+			for (int a = 0; a < 3; ++a) {
+				root_info->lo[a] = b.lo[a];
+				root_info->hi[a] = b.hi[a];
+			}
+			return;
+		}
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -206,59 +281,9 @@ __global__ void __launch_bounds__(256)
 	leaf_box[2 * j + 1] = make_float4(b.hi[0], b.hi[1], b.hi[2], 0.0f);
 }
 
-// ------------------------------------------------------------------------------------------------
-// 6. bottom-up refit
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_box_cg(const float4 *boxes, int64_t idx, Box &b) {
-	const float4 lo = __ldcg(boxes + 2 * idx);
-	const float4 hi = __ldcg(boxes + 2 * idx + 1);
-	b.lo[0] = lo.x;
-	b.lo[1] = lo.y;
-	b.lo[2] = lo.z;
-	b.hi[0] = hi.x;
-	b.hi[1] = hi.y;
-	b.hi[2] = hi.z;
-}
-
-__global__ void __launch_bounds__(256)
-    k_refit(Node *__restrict__ nodes, const int32_t *__restrict__ parent,
-            const int32_t *__restrict__ leaf_parent, const float4 *__restrict__ leaf_box,
-            float4 *__restrict__ node_box, uint32_t *__restrict__ flags, uint64_t n) {
-	const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= n)
-		return;
-	int32_t cur = leaf_parent[j];
-	while (cur >= 0) {
-		// the first thread to arrive stops; the second one owns the node (its sibling subtree is
-		// complete and, thanks to the fences, visible)
-		if (atomicAdd(&flags[cur], 1u) == 0u)
-			return;
-		__threadfence();
-		const int32_t c0 = nodes[cur].child0, c1 = nodes[cur].child1;
-		Box b0, b1;
-		if (c0 < 0)
-			load_box_cg(leaf_box, ~c0, b0);
-		else
-			load_box_cg(node_box, c0, b0);
-		if (c1 < 0)
-			load_box_cg(leaf_box, ~c1, b1);
-		else
-			load_box_cg(node_box, c1, b1);
-		float4 *nd = reinterpret_cast<float4 *>(nodes + cur);
-		nd[0] = make_float4(b0.lo[0], b0.lo[1], b0.lo[2], b0.hi[0]);
-		nd[1] = make_float4(b0.hi[1], b0.hi[2], b1.lo[0], b1.lo[1]);
-		nd[2] = make_float4(b1.lo[2], b1.hi[0], b1.hi[1], b1.hi[2]);
-		const Box u = box_union(b0, b1);
-		node_box[2 * (int64_t)cur] = make_float4(u.lo[0], u.lo[1], u.lo[2], 0.0f);
-		node_box[2 * (int64_t)cur + 1] = make_float4(u.hi[0], u.hi[1], u.hi[2], 0.0f);
-		__threadfence();
-		cur = parent[cur];
-	}
-}
-
 // single-triangle scene (bvh.hpp:165-181): a root whose first child is the triangle and whose
 // second child is a zero-area dummy record (det == 0 in intersect_tri, so it can never be hit)
-__global__ void k_single(Node *nodes, TriRec *recs, const float4 *leaf_box) {
+__global__ void k_single(Node *nodes, TriRec *recs, const float4 *leaf_box, RootInfo *root_info) {
 	Node nd;
 	const float4 lo = leaf_box[0], hi = leaf_box[1];
 	nd.lo0[0] = nd.lo1[0] = lo.x;
@@ -271,6 +296,13 @@ __global__ void k_single(Node *nodes, TriRec *recs, const float4 *leaf_box) {
 	nd.child1 = ~1;
 	nd.pad0 = nd.pad1 = 0;
 	nodes[0] = nd;
+	root_info->root = 0;
+	root_info->lo[0] = lo.x;
+	root_info->lo[1] = lo.y;
+	root_info->lo[2] = lo.z;
+	root_info->hi[0] = hi.x;
+	root_info->hi[1] = hi.y;
+	root_info->hi[2] = hi.z;
 	float4 *rec = reinterpret_cast<float4 *>(recs + 1);
 	rec[0] = make_float4(lo.x, lo.y, lo.z, __uint_as_float(0xffffffffu));
 	rec[1] = make_float4(0.f, 0.f, 0.f, lo.x);
@@ -305,11 +337,9 @@ int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 	PRT_CUDA(c, c->vals[0].reserve(n * 4));
 	PRT_CUDA(c, c->vals[1].reserve(n * 4));
 	PRT_CUDA(c, c->bounds.reserve(6 * 4));
-	PRT_CUDA(c, c->leaf_box.reserve(n * 32));
-	PRT_CUDA(c, c->node_box.reserve(n * 32));
-	PRT_CUDA(c, c->parent.reserve(n * 4));
-	PRT_CUDA(c, c->leaf_parent.reserve(n * 4));
-	PRT_CUDA(c, c->flags.reserve(n * 4));
+	PRT_CUDA(c, c->leaf_box.reserve(64));
+	PRT_CUDA(c, c->bound.reserve(n * 4));
+	PRT_CUDA(c, c->root_info.reserve(sizeof(RootInfo)));
 
 	const int stream_grid = (int)std::min<uint64_t>((n + TT - 1) / TT, (uint64_t)c->sm_count * 8);
 	const int bits = morton_bits_for(n);
@@ -329,21 +359,18 @@ int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 	}
 
 	const int g = (int)((n + 255) / 256);
-	k_leaves<<<g, 256, 0, s>>>(d_tris9, c->vals[cur].as<uint32_t>(), n, c->trirecs.as<TriRec>(),
-	                           c->leaf_box.as<float4>());
-	c->launches += 1;
 	if (n == 1) {
-		k_single<<<1, 1, 0, s>>>(c->nodes.as<Node>(), c->trirecs.as<TriRec>(), c->leaf_box.as<float4>());
-		c->launches += 1;
-	} else {
-		PRT_CUDA(c, cudaMemsetAsync(c->flags.p, 0, (n - 1) * 4, s));
-		k_karras<<<(int)((n - 1 + 255) / 256), 256, 0, s>>>(
-		    c->keys[cur].as<uint64_t>(), (int64_t)n, c->nodes.as<Node>(), c->parent.as<int32_t>(),
-		    c->leaf_parent.as<int32_t>());
-		k_refit<<<g, 256, 0, s>>>(c->nodes.as<Node>(), c->parent.as<int32_t>(),
-		                          c->leaf_parent.as<int32_t>(), c->leaf_box.as<float4>(),
-		                          c->node_box.as<float4>(), c->flags.as<uint32_t>(), n);
+		k_leaves<<<1, 256, 0, s>>>(d_tris9, c->vals[cur].as<uint32_t>(), n, c->trirecs.as<TriRec>(),
+		                           c->leaf_box.as<float4>());
+		k_single<<<1, 1, 0, s>>>(c->nodes.as<Node>(), c->trirecs.as<TriRec>(), c->leaf_box.as<float4>(),
+		                         c->root_info.as<RootInfo>());
 		c->launches += 2;
+	} else {
+		PRT_CUDA(c, cudaMemsetAsync(c->bound.p, 0xff, (n - 1) * 4, s));
+		k_hierarchy<<<g, 256, 0, s>>>(d_tris9, c->vals[cur].as<uint32_t>(), c->keys[cur].as<uint64_t>(),
+		                              (int)n, c->trirecs.as<TriRec>(), c->nodes.as<Node>(),
+		                              c->bound.as<int>(), c->root_info.as<RootInfo>());
+		c->launches += 1;
 	}
 	PRT_CUDA(c, cudaGetLastError());
 	return PRT_OK;

@@ -83,8 +83,8 @@ struct prt_b200 {
 	prt::DevBuf trirecs;   // prt::TriRec[n_tris]
 
 	// build scratch
-	prt::DevBuf keys[2], vals[2], sort_scratch, bounds, leaf_box, node_box, parent, leaf_parent,
-	    flags;
+	prt::DevBuf keys[2], vals[2], sort_scratch, bounds, leaf_box, bound, root_info;
+	int32_t root = 0; // index of the root node (the radix tree numbers nodes by split position)
 
 	// trace scratch
 	prt::DevBuf rays_dev[2], hits_dev[2], counter;

@@ -143,7 +143,8 @@ struct TravState {
 
 #define PRT_DONE ((int32_t)0x7fffffff)
 
-PRT_HD void trav_init(TravState &s, const RayC &r, const TraverseOpts &opt, uint64_t n_tris_scene) {
+PRT_HD void trav_init(TravState &s, const RayC &r, const TraverseOpts &opt, uint64_t n_tris_scene,
+                      int32_t root) {
 	s.t_best = INFINITY;
 	s.u_best = 0.0f;
 	s.v_best = 0.0f;
@@ -156,7 +157,7 @@ PRT_HD void trav_init(TravState &s, const RayC &r, const TraverseOpts &opt, uint
 	const float dmax = fmaxf(fmaxf(fabsf(r.d[0]), fabsf(r.d[1])), fabsf(r.d[2]));
 	s.slack_abs = fmul(fmul(opt.slack_ulps, 1.1920929e-7f), fdiv(omax, dmax));
 	s.sp = 0;
-	s.cur = n_tris_scene == 0 ? PRT_DONE : 0;
+	s.cur = n_tris_scene == 0 ? PRT_DONE : root;
 	s.n_nodes = 0;
 	s.n_tris = 0;
 }
@@ -253,11 +254,11 @@ PRT_HD void trav_step(TravState &s, StackEntry *stack, const Node *nodes, const 
 
 // Scalar driver (instrumented kernel and the host-side emulator): one ray start to finish.
 template <bool ANYHIT, bool WANT_UV, bool TRACK_PRIM, bool COUNT, bool FAST>
-PRT_HD void traverse(const Node *nodes, const TriRec *tris, uint64_t n_tris_scene, const RayC &r,
-                     const FastRay &fr, const TraverseOpts &opt, Hit &out) {
+PRT_HD void traverse(const Node *nodes, const TriRec *tris, uint64_t n_tris_scene, int32_t root,
+                     const RayC &r, const FastRay &fr, const TraverseOpts &opt, Hit &out) {
 	TravState s;
 	StackEntry stack[STACK_DEPTH];
-	trav_init(s, r, opt, n_tris_scene);
+	trav_init(s, r, opt, n_tris_scene, root);
 	while (s.cur != PRT_DONE)
 		trav_step<ANYHIT, WANT_UV, TRACK_PRIM, COUNT, FAST>(s, stack, nodes, tris, r, fr, opt);
 	out.t = s.t_best;

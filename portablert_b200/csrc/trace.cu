@@ -43,6 +43,7 @@ struct TraceParams {
 	float scene_absmax[3];
 	int fast; // 1: conservative FFMA test for internal culling where the ray qualifies
 	int refill; // re-fetch rays when fewer than this many lanes of a warp are still traversing
+	int32_t root;         // index of the root node
 	const uint32_t *perm; // ray processing order (reordered batches) or nullptr = identity
 };
 
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceParams P) {
 					r = make_ray(r6);
 					fr = make_fast_ray(r, P.scene_absmax);
 					fast = P.fast && fr.ok;
-					trav_init(s, r, opts, P.n_tris);
+					trav_init(s, r, opts, P.n_tris, P.root);
 					ray = i;
 					has_ray = true;
 				}
@@ -290,6 +291,7 @@ int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, c
 	P.rays = d_rays6;
 	P.n_rays = n;
 	P.n_tris = c->n_tris;
+	P.root = c->root;
 	P.uv = reinterpret_cast<float2 *>(out.soa.uv);
 	P.t = out.soa.t;
 	P.pid = out.soa.pid;

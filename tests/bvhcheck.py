@@ -4,7 +4,7 @@ import numpy as np
 NO_CHILD = 0x7FFFFFFF
 
 
-def check_bvh(nodes, trirecs, tris):
+def check_bvh(nodes, trirecs, tris, root=0):
     """Every triangle sits in exactly one leaf, every node is reached exactly once from the root,
     triangle records replay intersect_tri's edges bit-for-bit, child boxes are the EXACT union of
     what is below them.  Returns the tree depth."""
@@ -34,7 +34,7 @@ def check_bvh(nodes, trirecs, tris):
     seen_node = np.zeros(n_nodes, bool)
     # iterative post-order
     depth = 0
-    stack = [(0, 0, 1)]
+    stack = [(int(root), 0, 1)]
     while stack:
         node, state, d = stack.pop()
         depth = max(depth, d)

@@ -26,7 +26,7 @@ class Emu:
         L.emu_build.restype = C.c_void_p
         L.emu_build.argtypes = [C.c_void_p, C.c_uint64, C.c_int]
         L.emu_load.restype = C.c_void_p
-        L.emu_load.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        L.emu_load.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int32]
         L.emu_free.argtypes = [C.c_void_p]
         L.emu_num_nodes.restype = C.c_uint64
         L.emu_num_nodes.argtypes = [C.c_void_p]
@@ -43,12 +43,12 @@ class Emu:
         self.h = self.L.emu_build(tris.ctypes.data, len(tris), bits)
         return self
 
-    def load(self, nodes, tris):
+    def load(self, nodes, tris, root=0):
         self.free()
         nodes = np.ascontiguousarray(nodes)
         tris = np.ascontiguousarray(tris)
         self.n = tris.nbytes // 64
-        self.h = self.L.emu_load(nodes.ctypes.data, nodes.nbytes // 64, tris.ctypes.data, self.n)
+        self.h = self.L.emu_load(nodes.ctypes.data, nodes.nbytes // 64, tris.ctypes.data, self.n, root)
         return self
 
     def free(self):

@@ -22,13 +22,14 @@ struct Emu {
 	std::vector<Node> nodes;
 	std::vector<TriRec> tris;
 	uint64_t n = 0;
+	int32_t root = 0;
 	float absmax[3] = {0.f, 0.f, 0.f};
 	void bounds() {
 		for (int a = 0; a < 3; ++a)
 			absmax[a] = 0.f;
 		if (nodes.empty())
 			return;
-		const Node &r = nodes[0];
+		const Node &r = nodes[root];
 		for (int a = 0; a < 3; ++a) {
 			absmax[a] = fmaxf(fabsf(r.lo0[a]), fabsf(r.hi0[a]));
 			absmax[a] = fmaxf(absmax[a], fmaxf(fabsf(r.lo1[a]), fabsf(r.hi1[a])));
@@ -149,8 +150,9 @@ void emu_download(void *h, void *nodes, void *tris) {
 		std::memcpy(tris, e->tris.data(), e->n * sizeof(TriRec));
 }
 // load an externally built tree (e.g. one downloaded from the GPU) for host-side checking
-void *emu_load(const void *nodes, uint64_t n_nodes, const void *tris, uint64_t n_tris) {
+void *emu_load(const void *nodes, uint64_t n_nodes, const void *tris, uint64_t n_tris, int32_t root) {
 	Emu *e = new Emu();
+	e->root = root;
 	e->n = n_tris;
 	e->nodes.resize(n_nodes);
 	e->tris.resize(n_tris + 1);
@@ -176,13 +178,13 @@ void emu_trace(void *h, const float *rays6, uint64_t n, int prune, float slack_r
 		const FastRay fr = make_fast_ray(r, e->absmax);
 		const bool f = fast && fr.ok; // per ray here; the kernel votes per warp
 		if (anyhit && f)
-			traverse<true, false, false, false, true>(e->nodes.data(), e->tris.data(), e->n, r, fr, o, hit);
+			traverse<true, false, false, false, true>(e->nodes.data(), e->tris.data(), e->n, e->root, r, fr, o, hit);
 		else if (anyhit)
-			traverse<true, false, false, false, false>(e->nodes.data(), e->tris.data(), e->n, r, fr, o, hit);
+			traverse<true, false, false, false, false>(e->nodes.data(), e->tris.data(), e->n, e->root, r, fr, o, hit);
 		else if (f)
-			traverse<false, true, true, true, true>(e->nodes.data(), e->tris.data(), e->n, r, fr, o, hit);
+			traverse<false, true, true, true, true>(e->nodes.data(), e->tris.data(), e->n, e->root, r, fr, o, hit);
 		else
-			traverse<false, true, true, true, false>(e->nodes.data(), e->tris.data(), e->n, r, fr, o, hit);
+			traverse<false, true, true, true, false>(e->nodes.data(), e->tris.data(), e->n, e->root, r, fr, o, hit);
 		if (fastflag)
 			fastflag[i] = f;
 		if (t)
