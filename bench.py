@@ -132,7 +132,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception as e:
                 self.err = "reasons: " + repr(e)
-            time.sleep(0.002)
+            time.sleep(0.0005)
 
     def stop(self):
         self._stop.set()
@@ -440,8 +440,11 @@ def main():
                 "fraction can exceed the DRAM traffic; frac_of_l2 is the binding roofline" %
                 (backend.bvh_bytes / 1e6),
     }
-    build_bytes_per_tri = 36 + 36 + 12 + (6 if n_tris <= (1 << 22) else 8) * (8 + 24) + 36 + 64 + 32 \
-        + 2 * 64 + 64
+    # algorithmic HBM bytes per triangle: bounds 36 R; morton 36 R + 12 W; histograms
+    # 8 R; P sort passes x (12 R + 12 W); hierarchy kernel: 4 (index) + 36 (triangle) + 16 (keys) R,
+    # 64 W (record), 64 W (node halves), 24 R (sibling box), 8 (bound exchange)
+    passes = 4 if n_tris <= (1 << 15) else (6 if n_tris <= (1 << 22) else 8)
+    build_bytes_per_tri = 36 + 48 + 8 + 24 * passes + 56 + 64 + 64 + 24 + 8
     build = {"mtris_s": n_tris / (build_ms_mean * 1e-3) / 1e6, "ms": build_ms_mean,
              "bytes_per_tri": build_bytes_per_tri,
              "achieved_gbs": n_tris * build_bytes_per_tri / (build_ms_mean * 1e-3) / 1e9,
@@ -477,8 +480,10 @@ def main():
         "data": "synthetic",
         "config": {"workload": desc, "rays_per_gpu": n_rays, "tris": n_tris, "tag_mask": mask,
                    "l2": "flushed between timed steps (256 MiB memset)",
-                   "multi_gpu": "tris NCCL-broadcast, BVH built on every rank, rank r traces "
-                                "frame r (contiguous slice), hits gathered to rank 0 in e2e"},
+                   "multi_gpu": "tris NCCL-broadcast from rank 0, identical BVH built on every rank, "
+                                "batch = N frames, rank r traces the r-th contiguous slice; e2e: "
+                                "batch in host shared memory, each rank DMA's its own slice, hits "
+                                "land in ray order in the shared result"},
         "build_mtris_s": build["mtris_s"], "build": build,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline, "cpu_baseline": cpu,

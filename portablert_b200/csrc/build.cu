@@ -175,59 +175,176 @@ struct RootInfo {
 	int32_t pad;
 };
 
+// Shuffle phase shared by the warp and block levels: the alive lanes of the calling warp carry
+// subtrees that tile a contiguous leaf range in lane order.  Two NEIGHBOURING alive lanes are
+// siblings exactly when the lower one wants node r as a left child and the upper one wants node
+// l-1 (= that same r) as a right child; such pairs merge through shuffles -- no atomics, no fences.
+// Each round merges every mutually agreeing pair; the loop ends when a round merges nothing (the
+// remaining subtrees have siblings elsewhere or not complete yet).
+__device__ __forceinline__ void merge_neighbours(bool &alive, int &l, int &r, int32_t &ref, Box &b,
+                                                 const uint64_t *__restrict__ keys, int n,
+                                                 Node *nodes, RootInfo *root_info, unsigned lane) {
+	for (;;) {
+		const unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
+		if (alive && l == 0 && r == n - 1) { // the root: publish its index and the scene box
+			root_info->root = ref;
+#pragma unroll
+			for (int a = 0; a < 3; ++a) {
+				root_info->lo[a] = b.lo[a];
+				root_info->hi[a] = b.hi[a];
+			}
+			alive = false;
+		}
+		bool lc = false;
+		if (alive)
+			lc = (l == 0) || (r != n - 1 && delta_less(keys, r, l - 1));
+		const unsigned lc_mask = __ballot_sync(0xffffffffu, alive && lc);
+		const unsigned above = lane == 31 ? 0u : (alive_mask & ~((2u << lane) - 1u));
+		const unsigned below = alive_mask & ((1u << lane) - 1u);
+		const int next_lane = above ? __ffs(above) - 1 : -1;
+		const int prev_lane = below ? 31 - __clz(below) : -1;
+		const bool as_left = alive && lc && next_lane >= 0 && !((lc_mask >> next_lane) & 1u);
+		const bool as_right = alive && !lc && prev_lane >= 0 && ((lc_mask >> prev_lane) & 1u);
+		if (!__ballot_sync(0xffffffffu, as_left))
+			break;
+		const int p = as_left ? r : l - 1;
+		if (as_left || as_right) {
+			float2 *nd = reinterpret_cast<float2 *>(nodes + p) + (as_left ? 0 : 3);
+			nd[0] = make_float2(b.lo[0], b.lo[1]);
+			nd[1] = make_float2(b.lo[2], b.hi[0]);
+			nd[2] = make_float2(b.hi[1], b.hi[2]);
+			reinterpret_cast<int32_t *>(nodes + p)[as_left ? 12 : 13] = ref;
+		}
+		// the left lane carries the merged subtree on; it pulls the right lane's box and bound
+		const int srcl = as_left ? next_lane : (int)lane;
+		Box o;
+#pragma unroll
+		for (int a = 0; a < 3; ++a) {
+			o.lo[a] = __shfl_sync(0xffffffffu, b.lo[a], srcl);
+			o.hi[a] = __shfl_sync(0xffffffffu, b.hi[a], srcl);
+		}
+		const int r_other = __shfl_sync(0xffffffffu, r, srcl);
+		if (as_left) {
+			b = box_union(b, o);
+			r = r_other;
+			ref = p;
+		}
+		if (as_right)
+			alive = false;
+	}
+}
+
 // One thread per triangle (in Morton order).  It gathers its triangle, writes the 64-byte record
-// and then climbs: a subtree covering the sorted range [l, r] hangs under internal node r (as its
-// left child) if delta(r) < delta(l-1), else under node l-1 (as its right child) -- the binary
-// radix tree of Karras 2012 found bottom-up (Apetrei 2014), so no separate top-down hierarchy pass
-// and no parent pointers are needed.  The climbing thread writes ITS half of the parent's node
-// (child reference + the child's exact box), then swaps its range bound into bound[p]: the first
-// arrival finds -1 and retires, the second finds its sibling's bound, reads the sibling's box from
-// the node, and carries the union upwards.  Which thread arrives first does not influence what
-// is written, so the build is deterministic.
+// and then its subtree climbs: a subtree covering the sorted range [l, r] hangs under internal node
+// r (as its left child) if delta(r) < delta(l-1), else under node l-1 (as its right child) -- the
+// binary radix tree of Karras 2012 found bottom-up (Apetrei 2014), so no separate top-down
+// hierarchy pass and no parent pointers are needed.  Three levels of cooperation:
+//   warp   32 consecutive leaves: siblings are neighbouring lanes, merged with shuffles;
+//   block  the few subtrees each warp is left with are handed to warp 0 through shared memory and
+//          merged the same way (256 consecutive leaves);
+//   grid   whatever still waits for a sibling outside the block uses global memory: the carrier
+//          writes ITS half of the parent's node (child reference + exact box), then swaps its range
+//          bound into bound[p] with one acq_rel exchange -- the first arrival finds -1 and
+//          retires, the second finds its sibling's bound, reads the sibling's box from the node
+//          and carries the union upwards.
+// What is written never depends on which thread arrives first, so the build is deterministic.
 __global__ void __launch_bounds__(256)
     k_hierarchy(const float *__restrict__ tris9, const uint32_t *__restrict__ sorted_idx,
                 const uint64_t *__restrict__ keys, int n, TriRec *__restrict__ recs, Node *nodes,
                 int *bound, RootInfo *root_info) {
+	__shared__ int s_cnt[8];
+	__shared__ int s_l[32], s_r[32], s_ref[32];
+	__shared__ float s_box[6][32];
 	const int j = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-	if (j >= n)
-		return;
-	const uint32_t prim = sorted_idx[j];
-	const float *src = tris9 + (uint64_t)prim * 9;
-	float t[9];
+	const unsigned lane = threadIdx.x & 31;
+	const int w = threadIdx.x >> 5;
+	bool alive = j < n;
+	Box b;
+	if (alive) {
+		const uint32_t prim = sorted_idx[j];
+		const float *src = tris9 + (uint64_t)prim * 9;
+		float t[9];
 #pragma unroll
-	for (int k = 0; k < 9; ++k)
-		t[k] = __ldg(src + k);
-	Box b = tri_box(t);
-	float4 *rec = reinterpret_cast<float4 *>(recs + j);
-	// edges exactly as core.hpp:33-35 computes them
-	rec[0] = make_float4(t[0], t[1], t[2], __uint_as_float(prim));
-	rec[1] = make_float4(fsub(t[3], t[0]), fsub(t[4], t[1]), fsub(t[5], t[2]), b.lo[0]);
-	rec[2] = make_float4(fsub(t[6], t[0]), fsub(t[7], t[1]), fsub(t[8], t[2]), b.lo[1]);
-	rec[3] = make_float4(b.lo[2], b.hi[0], b.hi[1], b.hi[2]);
-
+		for (int k = 0; k < 9; ++k)
+			t[k] = __ldg(src + k);
+		b = tri_box(t);
+		float4 *rec = reinterpret_cast<float4 *>(recs + j);
+		// edges exactly as core.hpp:33-35 computes them
+		rec[0] = make_float4(t[0], t[1], t[2], __uint_as_float(prim));
+		rec[1] = make_float4(fsub(t[3], t[0]), fsub(t[4], t[1]), fsub(t[5], t[2]), b.lo[0]);
+		rec[2] = make_float4(fsub(t[6], t[0]), fsub(t[7], t[1]), fsub(t[8], t[2]), b.lo[1]);
+		rec[3] = make_float4(b.lo[2], b.hi[0], b.hi[1], b.hi[2]);
+	} else {
+#pragma unroll
+		for (int a = 0; a < 3; ++a)
+			b.lo[a] = b.hi[a] = 0.f;
+	}
 	int l = j, r = j;
 	int32_t ref = ~j;
+
+	// ---- warp level
+	merge_neighbours(alive, l, r, ref, b, keys, n, nodes, root_info, lane);
+
+	// ---- block level: hand the survivors (in leaf order) to warp 0 if they fit its 32 lanes
+	const unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
+	if (lane == 0)
+		s_cnt[w] = __popc(alive_mask);
+	__syncthreads();
+	int offset = 0, total = 0;
+#pragma unroll
+	for (int k = 0; k < 8; ++k) {
+		offset += k < w ? s_cnt[k] : 0;
+		total += s_cnt[k];
+	}
+	if (total > 1 && total <= 32) {
+		if (alive) {
+			const int idx = offset + __popc(alive_mask & ((1u << lane) - 1u));
+			s_l[idx] = l;
+			s_r[idx] = r;
+			s_ref[idx] = ref;
+#pragma unroll
+			for (int a = 0; a < 3; ++a) {
+				s_box[a][idx] = b.lo[a];
+				s_box[3 + a][idx] = b.hi[a];
+			}
+		}
+		__syncthreads();
+		alive = false; // warp 0 carries the survivors from here on
+		if (w == 0) {
+			alive = (int)lane < total;
+			if (alive) {
+				l = s_l[lane];
+				r = s_r[lane];
+				ref = s_ref[lane];
+#pragma unroll
+				for (int a = 0; a < 3; ++a) {
+					b.lo[a] = s_box[a][lane];
+					b.hi[a] = s_box[3 + a][lane];
+				}
+			}
+			merge_neighbours(alive, l, r, ref, b, keys, n, nodes, root_info, lane);
+		}
+	}
+	if (!alive)
+		return;
+
+	// ---- grid level
 	for (;;) {
 		const bool left_child = (l == 0) || (r != n - 1 && delta_less(keys, r, l - 1));
 		const int p = left_child ? r : l - 1;
-		float2 *nd = reinterpret_cast<float2 *>(nodes + p);
-		int32_t *ni = reinterpret_cast<int32_t *>(nodes + p);
-		if (left_child) { // floats 0..5 = child0 box, int 12 = child0
-			nd[0] = make_float2(b.lo[0], b.lo[1]);
-			nd[1] = make_float2(b.lo[2], b.hi[0]);
-			nd[2] = make_float2(b.hi[1], b.hi[2]);
-			ni[12] = ref;
-		} else { // floats 6..11 = child1 box, int 13 = child1
-			nd[3] = make_float2(b.lo[0], b.lo[1]);
-			nd[4] = make_float2(b.lo[2], b.hi[0]);
-			nd[5] = make_float2(b.hi[1], b.hi[2]);
-			ni[13] = ref;
-		}
-		__threadfence();
-		const int other = atomicExch(&bound[p], left_child ? l : r);
+		float2 *nd = reinterpret_cast<float2 *>(nodes + p) + (left_child ? 0 : 3);
+		nd[0] = make_float2(b.lo[0], b.lo[1]);
+		nd[1] = make_float2(b.lo[2], b.hi[0]);
+		nd[2] = make_float2(b.hi[1], b.hi[2]);
+		reinterpret_cast<int32_t *>(nodes + p)[left_child ? 12 : 13] = ref;
+		// release my half of the node, acquire the sibling's: one acq_rel exchange
+		int other;
+		asm volatile("atom.acq_rel.gpu.global.exch.b32 %0, [%1], %2;"
+		             : "=r"(other)
+		             : "l"(bound + p), "r"(left_child ? l : r)
+		             : "memory");
 		if (other == -1)
 			return; // first arrival: the sibling will carry on
-		__threadfence();
 		const float2 *sib = reinterpret_cast<const float2 *>(nodes + p) + (left_child ? 3 : 0);
 		const float2 s0 = __ldcg(sib), s1 = __ldcg(sib + 1), s2 = __ldcg(sib + 2);
 		Box o;
@@ -237,7 +354,7 @@ __global__ void __launch_bounds__(256)
 		o.hi[0] = s1.y;
 		o.hi[1] = s2.x;
 		o.hi[2] = s2.y;
-		b = box_union(b, o);
+		b = left_child ? box_union(b, o) : box_union(o, b); // always (left, right): bit-reproducible
 		if (left_child)
 			r = other;
 		else

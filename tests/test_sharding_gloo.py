@@ -78,3 +78,50 @@ def test_n_ranks_equal_one_rank(tmp_path, world, n_rays):
     for f in outs[0].dtype.names:  # field-wise: numpy does not preserve struct padding bytes
         a, b = np.ascontiguousarray(outs[0][f]), np.ascontiguousarray(outs[1][f])
         assert a.view(np.uint8).tobytes() == b.view(np.uint8).tobytes(), f
+
+
+def _shm_worker(rank, world, n_rays, tag):
+    sys.path.insert(0, ROOT)
+    from oracle import Oracle
+    from portablert_b200 import hitreg, scenes, sharding
+    import time
+    dt = hitreg.dtype(hitreg.T | hitreg.VALID)
+    if rank == 0:
+        shm = sharding.SharedHostBatch(tag, n_rays, dt, rank, world, True)
+        shm.rays[...] = scenes.pinhole_rays(n_rays // 10 + 1, 10)[:n_rays]
+        shm.rays.flush()
+        open(f"/dev/shm/{tag}_ready", "w").close()
+    else:
+        while not os.path.exists(f"/dev/shm/{tag}_ready"):
+            time.sleep(0.01)
+        shm = sharding.SharedHostBatch(tag, n_rays, dt, rank, world, False)
+    orc = Oracle().build(scenes.blob(20, 20))
+    o = orc.trace(np.asarray(shm.my_rays), threads=1)
+    mine = shm.my_hits
+    mine["t"] = o["t"]
+    mine["valid"] = o["valid"]
+    shm.hits.flush()
+    shm.close(unlink=False)
+
+
+def test_shared_host_batch_slices_assemble_in_ray_order():
+    """The multi-GPU host layout without GPUs: every rank fills only its own slice of the shared
+    result; together they must be exactly the single-process answer, in ray order."""
+    from oracle import Oracle
+    from portablert_b200 import hitreg, scenes
+    n_rays, world = 1003, 3
+    tag = "prt_b200_gloo_%d" % os.getpid()
+    try:
+        mp.spawn(_shm_worker, args=(world, n_rays, tag), nprocs=world, join=True)
+        dt = hitreg.dtype(hitreg.T | hitreg.VALID)
+        hits = np.memmap(f"/dev/shm/{tag}_hits", dt, "r", shape=(n_rays,))
+        rays = scenes.pinhole_rays(n_rays // 10 + 1, 10)[:n_rays]
+        ref = Oracle().build(scenes.blob(20, 20)).trace(rays)
+        assert np.array_equal(np.asarray(hits["t"]), ref["t"])
+        assert np.array_equal(np.asarray(hits["valid"]), ref["valid"])
+    finally:
+        for suffix in ("_rays", "_hits", "_ready"):
+            try:
+                os.unlink(f"/dev/shm/{tag}{suffix}")
+            except OSError:
+                pass

@@ -11,4 +11,4 @@ tris=scenes.sphere_field(10000)
 d=torch.from_numpy(tris).cuda(); torch.cuda.synchronize()
 for _ in range(2): b.set_tris_dev(d.data_ptr(),len(tris))
 PY
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_sweep_pass|k_refit|k_karras" -s 10 -c 5 -f -o gpurun_out/prof_build_10m python /tmp/b.py > gpurun_out/ncu_build10m.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/ncu_build10m.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_hierarchy" -s 1 -c 1 -f -o gpurun_out/prof_build_10m python /tmp/b.py > gpurun_out/ncu_build10m.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/ncu_build10m.log

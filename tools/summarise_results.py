@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Turn the bench JSON lines under gpurun_out/ into profiles/r01_results.md (numbers measured on
+the GPU box without a profiler attached)."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "gpurun_out")
+
+
+def load(name):
+    p = os.path.join(G, name)
+    if not os.path.exists(p):
+        return None
+    lines = [l for l in open(p).read().splitlines() if l.startswith("{")]
+    return json.loads(lines[-1]) if lines else None
+
+
+def main():
+    out = ["# Round 1 -- measured results (one B200 unless stated; no profiler attached)\n",
+           "Device-timed: rays resident in HBM, SoA outputs, CUDA events taken by the library on the "
+           "stream the kernels run on, L2 flushed (256 MiB memset) between timed steps, mean of the "
+           "timed steps.  e2e: host buffers in, host `HitReg` records out through "
+           "`prt_b200_nearest_hits` (pinned host memory, H2D + kernels + D2H inside the timed region).\n",
+           "| config | tris | rays | tags | trace ms | Mrays/s | nodes/ray | tris/ray | B/ray | "
+           "fetched GB/s | of L2 read peak | build ms | Mtris/s | e2e Mrays/s |",
+           "|---|---:|---:|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|"]
+    for cfg in ("c2", "c3", "c3b", "c5", "c4"):
+        d = load(f"bench_{cfg}.json")
+        if not d:
+            continue
+        r = d["roofline"]
+        out.append(f"| {cfg.upper()} | {d['config']['tris']:,} | {d['config']['rays_per_gpu']:,} | "
+                   f"mask {d['config']['tag_mask']} | {d['ms_per_step']:.3f} | {d['value']:.0f} | "
+                   f"{r['nodes_per_ray']:.1f} | {r['tris_per_ray']:.2f} | {r['bytes_per_ray']:.0f} | "
+                   f"{r['achieved']:.0f} | {r['frac_of_l2']:.2f} | {d['build']['ms']:.3f} | "
+                   f"{d['build']['mtris_s']:.0f} | {d['e2e']['value']:.0f} |")
+    d = load("bench_c2.json")
+    if d:
+        r = d["roofline"]
+        out.append(f"\nMeasured on the box in the same run: L2 read bandwidth {r['l2_read_gbs_measured']:.0f} GB/s "
+                   f"(32 MiB re-read), HBM read bandwidth {r['hbm_read_gbs_measured']:.0f} GB/s (2 GiB re-read); "
+                   f"roofline peak used for `roofline.frac`: {r['peak']} GB/s, {r['peak_source']}.  "
+                   f"Clocks during the timed region: {d['clocks']}.\n")
+        c = d.get("cpu_baseline") or {}
+        if c and "value" in c:
+            out.append(f"CPU reference beside it (unmodified reference CPU backend, oracle/_ref): "
+                       f"{c['value']:.1f} Mrays/s on {c['cores']} threads ({c['cpu']}), {c['sample']}; "
+                       f"`set_tris` {c['build_mtris_s']:.3f} Mtris/s (1 thread).  C2 ratios: device-timed "
+                       f"{d['value'] / c['value']:.0f}x, e2e (pinned) {d['e2e']['value'] / c['value']:.0f}x, "
+                       f"e2e (pageable) {d['e2e'].get('pageable_value', 0) / c['value']:.0f}x, build "
+                       f"{d['build']['mtris_s'] / c['build_mtris_s']:.0f}x.\n")
+        pm = d.get("per_mask_mrays_s")
+        if pm:
+            out.append("C2, all 31 tag combinations (device-timed Mrays/s): " +
+                       ", ".join(f"{k} {v:.0f}" for k, v in pm.items()) + "\n")
+    ref = load("bench_c2_ref.json")
+    if ref:
+        out.append(f"`bench.py --impl reference` (same box): {ref['value']:.1f} Mrays/s, "
+                   f"{ref['cpu_baseline']['cores']} threads, build {ref['build_mtris_s']:.3f} Mtris/s.\n")
+    rows = []
+    for n in (1, 2, 4, 8):
+        d = load("bench_c2.json") if n == 1 else load(f"bench_c2_n{n}.json")
+        if d:
+            rows.append(f"| {n} | {d['value']:.0f} | {d['ms_per_step']:.3f} | {d['e2e']['value']:.0f} | "
+                        f"{d['e2e']['ms_per_step']:.2f} |")
+    if rows:
+        out.append("## Multi-GPU (C2, weak scaling: N frames of 2 073 600 rays, one rank per GPU, torchrun)\n")
+        out.append("| GPUs | device-timed Mrays/s (whole job) | ms/step (max over ranks) | e2e Mrays/s | e2e ms/step |")
+        out.append("|---:|---:|---:|---:|---:|")
+        out += rows
+    open(os.path.join(ROOT, "profiles", "r01_results.md"), "w").write("\n".join(out) + "\n")
+    print("\n".join(out))
+
+
+if __name__ == "__main__":
+    main()
