@@ -14,6 +14,7 @@
 // HBM-bound integer/byte work: no tensor cores.  Algorithmic bytes per triangle are tallied in
 // DESIGN.md (build roofline).
 #include <algorithm>
+#include <cstdlib>
 
 #include "prt_ctx.h"
 
@@ -431,11 +432,20 @@ __global__ void k_single(Node *nodes, TriRec *recs, const float4 *leaf_box, Root
 // host driver
 // ------------------------------------------------------------------------------------------------
 static int morton_bits_for(uint64_t n) {
-	if (n <= (1ull << 15))
+	if (const char *e = std::getenv("PRT_B200_MORTON_BITS")) { // experiments: 1..21 bits per axis
+		const int b = std::atoi(e);
+		if (b >= 1 && b <= 21)
+			return b;
+	}
+	// Measured (profiles/r01_results.md): on all five configs 10 bits per axis give the same
+	// nodes/ray as 16 or 21 (equal keys are split by index, which keeps the subtrees balanced), so
+	// the resolution is chosen for robustness against small detailed objects in large scenes, not
+	// for these benchmarks; every 8 key bits cost one more sort pass.
+	if (n <= (1ull << 16))
 		return 10; // 30-bit keys, 4 passes
 	if (n <= (1ull << 22))
-		return 16; // 48-bit keys, 6 passes
-	return 21;     // 63-bit keys, 8 passes
+		return 13; // 39-bit keys, 5 passes
+	return 16;     // 48-bit keys, 6 passes (PRT_B200_MORTON_BITS=21: 63-bit keys, 8 passes)
 }
 
 int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {

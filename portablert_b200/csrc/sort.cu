@@ -90,19 +90,11 @@ __device__ __forceinline__ uint32_t block_exscan256(uint32_t v, uint32_t *ws) {
 	return res;
 }
 
-// histogram -> exclusive digit offsets, per pass (one block per pass)
-__global__ void __launch_bounds__(SO_THREADS) k_sweep_offsets(uint32_t *__restrict__ ghist) {
-	__shared__ uint32_t ws[32];
-	uint32_t *h = ghist + blockIdx.x * SO_RADIX;
-	const uint32_t v = h[threadIdx.x];
-	h[threadIdx.x] = block_exscan256(v, ws);
-}
-
 // ---- one pass --------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SO_THREADS)
     k_sweep_pass(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                  uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint64_t n,
-                 int shift, const uint32_t *__restrict__ digit_ofs /* [256] exclusive */,
+                 int shift, const uint32_t *__restrict__ digit_ofs /* [256] pass histogram */,
                  unsigned long long *status /* [n_tiles][256] */, uint32_t *tile_counter) {
 	__shared__ uint64_t s_keys[SO_TILE];
 	__shared__ uint32_t s_vals[SO_TILE];
@@ -200,7 +192,10 @@ __global__ void __launch_bounds__(SO_THREADS)
 	}
 	const uint32_t lb = block_exscan256(cnt, ws);
 	lbase[threadIdx.x] = lb;
-	gofs[threadIdx.x] = (long long)digit_ofs[threadIdx.x] + (long long)prefix - (long long)lb;
+	// global start of each digit = exclusive scan of the pass histogram (256 values: every tile
+	// redoes it instead of paying a separate launch)
+	const uint32_t dstart = block_exscan256(digit_ofs[threadIdx.x], ws);
+	gofs[threadIdx.x] = (long long)dstart + (long long)prefix - (long long)lb;
 	__syncthreads();
 
 	// stage the tile in digit order (stable), then write runs of consecutive addresses
@@ -248,8 +243,7 @@ int radix_sort_pairs(prt_b200 *c, DevBuf &scratch, uint64_t *const keys[2], uint
 	const int hgrid = (int)std::min<uint64_t>((n + SO_THREADS * 8 - 1) / (SO_THREADS * 8),
 	                                          (uint64_t)c->sm_count * 8);
 	k_sweep_hist<<<hgrid, SO_THREADS, 0, s>>>(keys[0], n, passes, ghist);
-	k_sweep_offsets<<<passes, SO_THREADS, 0, s>>>(ghist);
-	c->launches += 2;
+	c->launches += 1;
 	int cur = 0;
 	for (int p = 0; p < passes; ++p) {
 		k_sweep_pass<<<(unsigned)n_tiles, SO_THREADS, 0, s>>>(
