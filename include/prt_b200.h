@@ -132,6 +132,13 @@ int prt_b200_set_trace_opts(prt_b200 *ctx, const prt_trace_opts *opts);
  * sorted by a 24-bit origin/direction key unless most neighbouring rays already share their key.
  * prt_b200_sorted_batches counts the launches that were actually reordered. */
 int prt_b200_set_ray_sorting(prt_b200 *ctx, int mode);
+
+/* Compressed 4-wide nodes (64 B per four children, 8-bit quantised boxes, used only for
+ * conservative culling): 0 = never build/use them, 1 = every batch, 2 = batches that were found
+ * incoherent and reordered (default; env PRT_B200_WIDE).  Takes effect at the next set_tris. */
+int prt_b200_set_wide_nodes(prt_b200 *ctx, int mode);
+/* copies the wide node array (64 B per binary node index) to the host, for structural tests */
+int prt_b200_download_wide(const prt_b200 *ctx, void *nodes4_out);
 uint64_t prt_b200_sorted_batches(const prt_b200 *ctx);
 
 /* Instrumented traversal (never used in timed runs): per ray, counts[2i] = internal nodes

@@ -46,6 +46,8 @@ SYMBOLS = {
                                          C.POINTER(HitLayout), C.c_void_p, C.POINTER(C.c_float)]),
     "prt_b200_set_trace_opts": (C.c_int, [C.c_void_p, C.POINTER(TraceOpts)]),
     "prt_b200_set_ray_sorting": (C.c_int, [C.c_void_p, C.c_int]),
+    "prt_b200_set_wide_nodes": (C.c_int, [C.c_void_p, C.c_int]),
+    "prt_b200_download_wide": (C.c_int, [C.c_void_p, C.c_void_p]),
     "prt_b200_sorted_batches": (C.c_uint64, [C.c_void_p]),
     "prt_b200_trace_count_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "prt_b200_num_tris": (C.c_uint64, [C.c_void_p]),

@@ -159,6 +159,17 @@ class CUDABackend(Backend):
         self._need()
         self._check(lib().prt_b200_set_ray_sorting(self._h, int(mode)))
 
+    def set_wide_nodes(self, mode: int):
+        """0 never, 1 always, 2 only for reordered (incoherent) batches; applies from the next set_tris."""
+        self._need()
+        self._check(lib().prt_b200_set_wide_nodes(self._h, int(mode)))
+
+    def download_wide(self):
+        self._need()
+        out = np.zeros((self.num_nodes, 64), np.uint8)
+        self._check(lib().prt_b200_download_wide(self._h, out.ctypes.data))
+        return out
+
     @property
     def sorted_batches(self):
         return lib().prt_b200_sorted_batches(self._h)

@@ -100,6 +100,8 @@ int prt_b200_create(prt_b200 **out, int device) {
 	c->sm_count = prop.multiProcessorCount;
 	if (const char *e = std::getenv("PRT_B200_FAST_BOXES"))
 		c->fast_boxes = std::atoi(e) != 0;
+	if (const char *e = std::getenv("PRT_B200_WIDE"))
+		c->wide_mode = std::max(0, std::min(2, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_SORT_RAYS"))
 		c->sort_rays = std::max(0, std::min(2, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_REFILL"))
@@ -116,7 +118,7 @@ void prt_b200_destroy(prt_b200 *c) {
 		cudaSetDevice(c->device);
 	if (c->stream)
 		cudaStreamSynchronize(c->stream);
-	prt::DevBuf *bufs[] = {&c->tris_raw, &c->nodes,    &c->trirecs,     &c->keys[0],     &c->keys[1],
+	prt::DevBuf *bufs[] = {&c->tris_raw, &c->nodes,    &c->trirecs,     &c->nodes4,     &c->keys[0],     &c->keys[1],
 	                       &c->vals[0],  &c->vals[1],  &c->sort_scratch, &c->bounds,
 	                       &c->leaf_box, &c->bound,    &c->root_info,
 	                       &c->rays_dev[0], &c->rays_dev[1], &c->hits_dev[0], &c->hits_dev[1],
@@ -157,6 +159,13 @@ int prt_b200_device_name(const prt_b200 *c, char *buf, size_t cap) {
 	std::strncpy(buf, c->name.c_str(), cap - 1);
 	buf[cap - 1] = 0;
 	return (int)std::min(c->name.size(), cap - 1);
+}
+
+int prt_b200_set_wide_nodes(prt_b200 *c, int mode) {
+	if (!c || mode < 0 || mode > 2)
+		return fail(c, PRT_E_ARG, "set_wide_nodes: mode must be 0, 1 or 2");
+	c->wide_mode = mode;
+	return PRT_OK;
 }
 
 int prt_b200_set_ray_sorting(prt_b200 *c, int mode) {
@@ -466,6 +475,19 @@ uint64_t prt_b200_num_nodes(const prt_b200 *c) { return c ? c->n_nodes : 0; }
 int32_t prt_b200_bvh_root(const prt_b200 *c) { return c ? c->root : 0; }
 uint64_t prt_b200_bvh_bytes(const prt_b200 *c) {
 	return c ? c->n_nodes * sizeof(prt::Node) + c->n_tris * sizeof(prt::TriRec) : 0;
+}
+int prt_b200_download_wide(const prt_b200 *cc, void *nodes4_out) {
+	prt_b200 *c = const_cast<prt_b200 *>(cc);
+	if (!c || !nodes4_out)
+		return PRT_E_ARG;
+	if (!c->wide_built)
+		return fail(c, PRT_E_ARG, "download_wide: no wide nodes were built for this scene");
+	PRT_CUDA(c, cudaSetDevice(c->device));
+	PRT_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (c->n_nodes)
+		PRT_CUDA(c, cudaMemcpy(nodes4_out, c->nodes4.p, c->n_nodes * sizeof(prt::Node4),
+		                       cudaMemcpyDeviceToHost));
+	return PRT_OK;
 }
 uint64_t prt_b200_launch_count(const prt_b200 *c) { return c ? c->launches : 0; }
 float prt_b200_last_build_ms(const prt_b200 *c) { return c ? c->last_build_ms : 0.f; }

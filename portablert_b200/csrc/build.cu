@@ -429,6 +429,63 @@ __global__ void k_single(Node *nodes, TriRec *recs, const float4 *leaf_box, Root
 }
 
 // ------------------------------------------------------------------------------------------------
+// 6. compressed 4-wide nodes: wide node i = the grandchildren of binary node i, 8-bit boxes
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Node load_node(const Node *nodes, int32_t i) {
+	Node nd;
+	const float4 *p = reinterpret_cast<const float4 *>(nodes + i);
+	float4 *q = reinterpret_cast<float4 *>(&nd);
+	q[0] = __ldg(p);
+	q[1] = __ldg(p + 1);
+	q[2] = __ldg(p + 2);
+	q[3] = __ldg(p + 3);
+	return nd;
+}
+
+__global__ void __launch_bounds__(256)
+    k_wide(const Node *__restrict__ nodes, int n_nodes, Node4 *__restrict__ out) {
+	const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+	if (i >= n_nodes)
+		return;
+	const Node nd = load_node(nodes, i);
+	WideChild ch[4];
+	int cnt = 0;
+#pragma unroll
+	for (int side = 0; side < 2; ++side) {
+		const int32_t c = side ? nd.child1 : nd.child0;
+		const float *lo = side ? nd.lo1 : nd.lo0, *hi = side ? nd.hi1 : nd.hi0;
+		if (c >= 0) { // internal: take its two children
+			const Node g = load_node(nodes, c);
+#pragma unroll
+			for (int a = 0; a < 3; ++a) {
+				ch[cnt].lo[a] = g.lo0[a];
+				ch[cnt].hi[a] = g.hi0[a];
+				ch[cnt + 1].lo[a] = g.lo1[a];
+				ch[cnt + 1].hi[a] = g.hi1[a];
+			}
+			ch[cnt].ref = g.child0;
+			ch[cnt + 1].ref = g.child1;
+			cnt += 2;
+		} else { // leaf: stays a direct child
+#pragma unroll
+			for (int a = 0; a < 3; ++a) {
+				ch[cnt].lo[a] = lo[a];
+				ch[cnt].hi[a] = hi[a];
+			}
+			ch[cnt].ref = c;
+			cnt += 1;
+		}
+	}
+	const Node4 w = make_node4(ch, cnt);
+	const float4 *src = reinterpret_cast<const float4 *>(&w);
+	float4 *dst = reinterpret_cast<float4 *>(out + i);
+	dst[0] = src[0];
+	dst[1] = src[1];
+	dst[2] = src[2];
+	dst[3] = src[3];
+}
+
+// ------------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------------
 static int morton_bits_for(uint64_t n) {
@@ -452,6 +509,7 @@ int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 	cudaStream_t s = c->stream;
 	c->n_tris = n;
 	c->n_nodes = n == 0 ? 0 : (n == 1 ? 1 : n - 1);
+	c->wide_built = false;
 	if (n == 0)
 		return PRT_OK;
 	if (n > 0x7ffffffeull)
@@ -497,6 +555,13 @@ int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 		k_hierarchy<<<g, 256, 0, s>>>(d_tris9, c->vals[cur].as<uint32_t>(), c->keys[cur].as<uint64_t>(),
 		                              (int)n, c->trirecs.as<TriRec>(), c->nodes.as<Node>(),
 		                              c->bound.as<int>(), c->root_info.as<RootInfo>());
+		c->launches += 1;
+	}
+	c->wide_built = c->wide_mode == 1 || (c->wide_mode == 2 && n >= (1ull << 20));
+	if (c->wide_built) {
+		PRT_CUDA(c, c->nodes4.reserve(c->n_nodes * sizeof(Node4)));
+		k_wide<<<(int)((c->n_nodes + 255) / 256), 256, 0, s>>>(c->nodes.as<Node>(), (int)c->n_nodes,
+		                                                      c->nodes4.as<Node4>());
 		c->launches += 1;
 	}
 	PRT_CUDA(c, cudaGetLastError());

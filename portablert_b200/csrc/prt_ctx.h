@@ -81,6 +81,8 @@ struct prt_b200 {
 	prt::DevBuf tris_raw;  // staged copy of the caller's 36-byte records (host entry point only)
 	prt::DevBuf nodes;     // prt::Node[n_nodes]
 	prt::DevBuf trirecs;   // prt::TriRec[n_tris]
+	prt::DevBuf nodes4;    // prt::Node4[n_nodes]: compressed 4-wide view of the same tree
+	int wide_mode = 2;     // env PRT_B200_WIDE: 0 never built/used, 1 always, 2 incoherent batches only
 
 	// build scratch
 	prt::DevBuf keys[2], vals[2], sort_scratch, bounds, leaf_box, bound, root_info;
@@ -97,7 +99,8 @@ struct prt_b200 {
 	unsigned long long *probe_dev = nullptr;     // ... and their device view
 	int sort_rays = 2; // env PRT_B200_SORT_RAYS: 0 never, 1 always, 2 auto (only incoherent batches)
 	float scene_lo[3] = {0.f, 0.f, 0.f}, scene_hi[3] = {0.f, 0.f, 0.f};
-	uint64_t sorted_batches = 0, unsorted_batches = 0;
+	uint64_t sorted_batches = 0, unsorted_batches = 0, wide_batches = 0;
+	bool wide_built = false, last_wide = false;
 	prt::PinnedBuf rays_pin[2], hits_pin[2];
 
 	prt_trace_opts opts{1, 1e-4f, 64.0f};

@@ -79,6 +79,104 @@ struct Box {
 	float lo[3], hi[3];
 };
 
+// ---------------------------------------------------------------------------------------------
+// Compressed 4-wide node (64 B, four 16-byte loads): the four grandchildren of a binary node with
+// their boxes quantised to 8 bits per plane inside the node's own bounds (origin p, one power-of-two
+// scale per axis).  One fetch decides four subtrees, i.e. two levels of the binary tree, with the
+// same 64 bytes a binary node needs for two.  Quantised boxes are only ever used for CONSERVATIVE
+// internal culling (prt_traverse.cuh); a triangle's own box is always taken exact from its
+// TriRec, so results cannot change.  Wide node i describes the subtree of binary node i (same
+// numbering, no allocation pass); only every other level is ever reached from the root.
+//   child >= 0 internal (wide/binary node index), < 0 leaf ~triangle record, PRT_NO_CHILD empty
+struct __attribute__((aligned(16))) Node4 {
+	float p[3];
+	uint8_t e[3]; // biased exponents: scale[a] = 2^(e[a] - 127)
+	uint8_t pad0;
+	uint8_t qlo[3][4]; // [axis][child]
+	uint8_t qhi[3][4];
+	int32_t child[4];
+	uint32_t pad1[2];
+};
+static_assert(sizeof(Node4) == 64, "Node4 must be 64 bytes");
+
+PRT_HD float pow2_from_biased(uint32_t e) {
+	const uint32_t bits = e << 23;
+	float f;
+#if defined(__CUDA_ARCH__)
+	f = __uint_as_float(bits);
+#else
+	__builtin_memcpy(&f, &bits, 4);
+#endif
+	return f;
+}
+
+struct WideChild {
+	float lo[3], hi[3];
+	int32_t ref;
+};
+
+// Quantise up to four children.  Guarantees for every child and axis, in binary32 arithmetic with
+// the canonical dequantisation fma(q, scale, p):  lo' <= lo  and  hi' >= hi, except that hi' may
+// fall short of hi by at most half an ulp of the coordinate when q saturates at 255 (covered by
+// the traversal's error margin like every other rounding of coordinates).
+PRT_HD Node4 make_node4(const WideChild *ch, int count) {
+	Node4 nd;
+	float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+	for (int k = 0; k < count; ++k)
+		for (int a = 0; a < 3; ++a) {
+			lo[a] = fminf(lo[a], ch[k].lo[a]);
+			hi[a] = fmaxf(hi[a], ch[k].hi[a]);
+		}
+	float scale[3];
+	for (int a = 0; a < 3; ++a) {
+		nd.p[a] = lo[a];
+		const float ext = fsub(hi[a], lo[a]);
+		// smallest power of two s with 255 * s >= ext
+		int k = 0;
+		const float m = frexpf(fdiv(ext, 255.0f), &k); // ext/255 = m * 2^k, m in [0.5, 1)
+		(void)m;
+		int eb = k + 127;
+		if (!(ext > 0.0f))
+			eb = 1;
+		if (eb < 1)
+			eb = 1;
+		if (eb > 254 || !(ext < INFINITY))
+			eb = 254;
+		nd.e[a] = (uint8_t)eb;
+		scale[a] = pow2_from_biased((uint32_t)eb);
+	}
+	nd.pad0 = 0;
+	nd.pad1[0] = nd.pad1[1] = 0;
+	for (int k = 0; k < 4; ++k) {
+		if (k < count) {
+			nd.child[k] = ch[k].ref;
+			for (int a = 0; a < 3; ++a) {
+				float ql = floorf(fdiv(fsub(ch[k].lo[a], nd.p[a]), scale[a]));
+				ql = fminf(fmaxf(ql, 0.0f), 255.0f);
+				if (ql > 0.0f && fmaf(ql, scale[a], nd.p[a]) > ch[k].lo[a])
+					ql -= 1.0f;
+				float qh = ceilf(fdiv(fsub(ch[k].hi[a], nd.p[a]), scale[a]));
+				qh = fminf(fmaxf(qh, 0.0f), 255.0f);
+				if (qh < 255.0f && fmaf(qh, scale[a], nd.p[a]) < ch[k].hi[a])
+					qh += 1.0f;
+				if (!(ql == ql))
+					ql = 0.0f; // NaN coordinates: widest box
+				if (!(qh == qh))
+					qh = 255.0f;
+				nd.qlo[a][k] = (uint8_t)ql;
+				nd.qhi[a][k] = (uint8_t)qh;
+			}
+		} else {
+			nd.child[k] = PRT_NO_CHILD;
+			for (int a = 0; a < 3; ++a) {
+				nd.qlo[a][k] = 255; // inverted box
+				nd.qhi[a][k] = 0;
+			}
+		}
+	}
+	return nd;
+}
+
 // make_aabb, bvh.hpp:28-37 (same nesting: min(a, min(b, c)))
 PRT_HD Box tri_box(const float *t9) {
 	Box b;

@@ -6,7 +6,9 @@
 
 namespace prt {
 
-constexpr int STACK_DEPTH = 96; // Karras tree over (64-bit key . 32-bit index): depth <= 96
+// Radix tree over (64-bit key . 32-bit index): depth <= 96, one push per level; the 4-wide nodes
+// push up to three entries per (two-level) step: 3 * 48 = 144
+constexpr int STACK_DEPTH = 152;
 
 struct TraverseOpts {
 	int prune;
@@ -162,11 +164,96 @@ PRT_HD void trav_init(TravState &s, const RayC &r, const TraverseOpts &opt, uint
 	s.n_tris = 0;
 }
 
-template <bool ANYHIT, bool WANT_UV, bool TRACK_PRIM, bool COUNT, bool FAST>
+// One step through a compressed 4-wide node (FAST rays only): dequantise the four child boxes
+// straight into ray parameters, t = fma(q, scale*idir, fma(p, idir, c)), test them with the
+// conservative margin (twice the binary node's: the quantiser may be half an ulp short at q = 255
+// and one more product is rounded), enter the nearest hit child and push the others farthest
+// first.  Returns true when nothing was hit (the caller pops).
+PRT_HD bool wide_node_step(TravState &s, StackEntry *stack, const Node4 *nodes4, const FastRay &fr) {
+	const char *np = reinterpret_cast<const char *>(nodes4 + s.cur);
+	const Vec4 v0 = ld16(np), v1 = ld16(np + 16), v2 = ld16(np + 32), v3 = ld16(np + 48);
+	const uint32_t ebits = f2u(v0.w);
+	const uint32_t qw[6] = {f2u(v1.x), f2u(v1.y), f2u(v1.z), f2u(v1.w), f2u(v2.x), f2u(v2.y)};
+	const int32_t ch[4] = {(int32_t)f2u(v2.z), (int32_t)f2u(v2.w), (int32_t)f2u(v3.x),
+	                       (int32_t)f2u(v3.y)};
+	const float pp[3] = {v0.x, v0.y, v0.z};
+	float sc[3], bb[3];
+#pragma unroll
+	for (int a = 0; a < 3; ++a) {
+		sc[a] = fmul(pow2_from_biased((ebits >> (8 * a)) & 0xffu), fr.idir[a]);
+#if defined(__CUDA_ARCH__)
+		bb[a] = __fmaf_rn(pp[a], fr.idir[a], fr.c[a]);
+#else
+		bb[a] = fmaf(pp[a], fr.idir[a], fr.c[a]);
+#endif
+	}
+	const float M4 = fadd(fr.M, fr.M);
+	const float lim = fadd(s.limitM, fr.M);
+	float t[4];
+	int32_t c[4];
+	int nh = 0;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		float tmin = -INFINITY, tmax = INFINITY;
+#pragma unroll
+		for (int a = 0; a < 3; ++a) {
+			const float ql = (float)((qw[a] >> (8 * k)) & 0xffu);
+			const float qh = (float)((qw[3 + a] >> (8 * k)) & 0xffu);
+#if defined(__CUDA_ARCH__)
+			const float tl = __fmaf_rn(ql, sc[a], bb[a]), th = __fmaf_rn(qh, sc[a], bb[a]);
+#else
+			const float tl = fmaf(ql, sc[a], bb[a]), th = fmaf(qh, sc[a], bb[a]);
+#endif
+			tmin = fmaxf(tmin, fminf(tl, th));
+			tmax = fminf(tmax, fmaxf(tl, th));
+		}
+		const bool hit = (tmax >= -M4) && (fsub(tmin, tmax) <= fadd(M4, M4)) && !(tmin > lim) &&
+		                 (ch[k] != PRT_NO_CHILD);
+		t[k] = hit ? tmin : INFINITY;
+		c[k] = ch[k];
+		nh += hit ? 1 : 0;
+	}
+	if (nh == 0)
+		return true;
+	// sort the (up to four) hits by entry distance: 5-comparator network, misses carry +inf
+#define PRT_CSWAP(i, j)                                                                            \
+	{                                                                                              \
+		const bool sw = t[j] < t[i];                                                               \
+		const float ti = sw ? t[j] : t[i], tj = sw ? t[i] : t[j];                                  \
+		const int32_t ci = sw ? c[j] : c[i], cj = sw ? c[i] : c[j];                                \
+		t[i] = ti;                                                                                 \
+		t[j] = tj;                                                                                 \
+		c[i] = ci;                                                                                 \
+		c[j] = cj;                                                                                 \
+	}
+	PRT_CSWAP(0, 1)
+	PRT_CSWAP(2, 3)
+	PRT_CSWAP(0, 2)
+	PRT_CSWAP(1, 3)
+	PRT_CSWAP(1, 2)
+#undef PRT_CSWAP
+#pragma unroll
+	for (int k = 3; k >= 1; --k) {
+		if (k < nh) {
+			stack[s.sp].node = (uint32_t)c[k];
+			stack[s.sp].tmin_bits = f2u(t[k]);
+			++s.sp;
+		}
+	}
+	s.cur = c[0];
+	return false;
+}
+
+template <bool ANYHIT, bool WANT_UV, bool TRACK_PRIM, bool COUNT, bool FAST, bool WIDE = false>
 PRT_HD void trav_step(TravState &s, StackEntry *stack, const Node *nodes, const TriRec *tris,
-                      const RayC &r, const FastRay &fr, const TraverseOpts &opt) {
+                      const RayC &r, const FastRay &fr, const TraverseOpts &opt,
+                      const Node4 *nodes4 = nullptr) {
 	bool pop = true;
-	if (s.cur >= 0) {
+	if (WIDE && s.cur >= 0) {
+		if (COUNT)
+			++s.n_nodes;
+		pop = wide_node_step(s, stack, nodes4, fr);
+	} else if (s.cur >= 0) {
 		const char *np = reinterpret_cast<const char *>(nodes + s.cur);
 		const Vec4 a = ld16(np), b = ld16(np + 16), c = ld16(np + 32), d = ld16(np + 48);
 		const int32_t c0 = (int32_t)f2u(d.x), c1 = (int32_t)f2u(d.y);
@@ -244,7 +331,8 @@ PRT_HD void trav_step(TravState &s, StackEntry *stack, const Node *nodes, const 
 		while (s.sp > 0) {
 			--s.sp;
 			// a stacked entry distance is a lower bound within M on the fast path
-			if (!(u2f(stack[s.sp].tmin_bits) > (FAST ? s.limitM : s.limit))) {
+			const float lim = WIDE ? fadd(s.limitM, fr.M) : (FAST ? s.limitM : s.limit);
+			if (!(u2f(stack[s.sp].tmin_bits) > lim)) {
 				s.cur = (int32_t)stack[s.sp].node;
 				break;
 			}
@@ -253,14 +341,16 @@ PRT_HD void trav_step(TravState &s, StackEntry *stack, const Node *nodes, const 
 }
 
 // Scalar driver (instrumented kernel and the host-side emulator): one ray start to finish.
-template <bool ANYHIT, bool WANT_UV, bool TRACK_PRIM, bool COUNT, bool FAST>
+template <bool ANYHIT, bool WANT_UV, bool TRACK_PRIM, bool COUNT, bool FAST, bool WIDE = false>
 PRT_HD void traverse(const Node *nodes, const TriRec *tris, uint64_t n_tris_scene, int32_t root,
-                     const RayC &r, const FastRay &fr, const TraverseOpts &opt, Hit &out) {
+                     const RayC &r, const FastRay &fr, const TraverseOpts &opt, Hit &out,
+                     const Node4 *nodes4 = nullptr) {
 	TravState s;
 	StackEntry stack[STACK_DEPTH];
 	trav_init(s, r, opt, n_tris_scene, root);
 	while (s.cur != PRT_DONE)
-		trav_step<ANYHIT, WANT_UV, TRACK_PRIM, COUNT, FAST>(s, stack, nodes, tris, r, fr, opt);
+		trav_step<ANYHIT, WANT_UV, TRACK_PRIM, COUNT, FAST, WIDE>(s, stack, nodes, tris, r, fr, opt,
+		                                                          nodes4);
 	out.t = s.t_best;
 	out.u = s.u_best;
 	out.v = s.v_best;

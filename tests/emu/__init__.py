@@ -31,8 +31,9 @@ class Emu:
         L.emu_num_nodes.restype = C.c_uint64
         L.emu_num_nodes.argtypes = [C.c_void_p]
         L.emu_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.emu_download_wide.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_float, C.c_float,
-                                C.c_int, C.c_int] + [C.c_void_p] * 8
+                                C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8
         self.L = L
         self.h = None
 
@@ -63,7 +64,13 @@ class Emu:
         self.L.emu_download(self.h, nodes.ctypes.data, tris.ctypes.data)
         return nodes, tris
 
-    def trace(self, rays, prune=1, slack_rel=1e-4, slack_ulps=64.0, anyhit=False, fast=True):
+    def download_wide(self):
+        nn = self.L.emu_num_nodes(self.h)
+        out = np.zeros((nn, 64), np.uint8)
+        self.L.emu_download_wide(self.h, out.ctypes.data)
+        return out
+
+    def trace(self, rays, prune=1, slack_rel=1e-4, slack_ulps=64.0, anyhit=False, fast=True, wide=False):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
         n = len(rays)
         o = {k: np.empty(n, np.float32) for k in ("t", "u", "v")}
@@ -73,7 +80,7 @@ class Emu:
         cnt = np.zeros((n, 2), np.uint32)
         ff = np.zeros(n, np.uint8)
         self.L.emu_trace(self.h, rays.ctypes.data, n, int(prune), slack_rel, slack_ulps,
-                         int(anyhit), int(fast), o["t"].ctypes.data, o["u"].ctypes.data, o["v"].ctypes.data,
+                         int(anyhit), int(fast), int(wide), o["t"].ctypes.data, o["u"].ctypes.data, o["v"].ctypes.data,
                          o["pid"].ctypes.data, o["valid"].ctypes.data, p.ctypes.data,
                          cnt.ctypes.data, ff.ctypes.data)
         o["fast"] = ff.astype(bool)

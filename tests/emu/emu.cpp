@@ -20,11 +20,45 @@ using namespace prt;
 namespace {
 struct Emu {
 	std::vector<Node> nodes;
+	std::vector<Node4> nodes4;
 	std::vector<TriRec> tris;
 	uint64_t n = 0;
 	int32_t root = 0;
 	float absmax[3] = {0.f, 0.f, 0.f};
+	void widen() { // same gathering as k_wide (build.cu); the quantiser itself is shared source
+		nodes4.resize(nodes.size());
+		for (size_t i = 0; i < nodes.size(); ++i) {
+			const Node &nd = nodes[i];
+			WideChild ch[4];
+			int cnt = 0;
+			for (int side = 0; side < 2; ++side) {
+				const int32_t c = side ? nd.child1 : nd.child0;
+				const float *lo = side ? nd.lo1 : nd.lo0, *hi = side ? nd.hi1 : nd.hi0;
+				if (c >= 0) {
+					const Node &g = nodes[c];
+					for (int a = 0; a < 3; ++a) {
+						ch[cnt].lo[a] = g.lo0[a];
+						ch[cnt].hi[a] = g.hi0[a];
+						ch[cnt + 1].lo[a] = g.lo1[a];
+						ch[cnt + 1].hi[a] = g.hi1[a];
+					}
+					ch[cnt].ref = g.child0;
+					ch[cnt + 1].ref = g.child1;
+					cnt += 2;
+				} else {
+					for (int a = 0; a < 3; ++a) {
+						ch[cnt].lo[a] = lo[a];
+						ch[cnt].hi[a] = hi[a];
+					}
+					ch[cnt].ref = c;
+					cnt += 1;
+				}
+			}
+			nodes4[i] = make_node4(ch, cnt);
+		}
+	}
 	void bounds() {
+		widen();
 		for (int a = 0; a < 3; ++a)
 			absmax[a] = 0.f;
 		if (nodes.empty())
@@ -142,6 +176,11 @@ void *emu_build(const float *tris9, uint64_t n, int bits) {
 
 void emu_free(void *h) { delete static_cast<Emu *>(h); }
 uint64_t emu_num_nodes(void *h) { return static_cast<Emu *>(h)->nodes.size(); }
+void emu_download_wide(void *h, void *nodes4) {
+	Emu *e = static_cast<Emu *>(h);
+	if (nodes4 && !e->nodes4.empty())
+		std::memcpy(nodes4, e->nodes4.data(), e->nodes4.size() * sizeof(Node4));
+}
 void emu_download(void *h, void *nodes, void *tris) {
 	Emu *e = static_cast<Emu *>(h);
 	if (nodes && !e->nodes.empty())
@@ -168,7 +207,7 @@ void *emu_load(const void *nodes, uint64_t n_nodes, const void *tris, uint64_t n
 // SoA outputs like the device entry point; counts (2 per ray) may be NULL.  anyhit=1 emulates the
 // `valid`-only specialisation.
 void emu_trace(void *h, const float *rays6, uint64_t n, int prune, float slack_rel, float slack_ulps,
-               int anyhit, int fast, float *t, float *u, float *v, uint32_t *pid, uint8_t *valid, float *p,
+               int anyhit, int fast, int wide, float *t, float *u, float *v, uint32_t *pid, uint8_t *valid, float *p,
                uint32_t *counts, uint8_t *fastflag) {
 	Emu *e = static_cast<Emu *>(h);
 	TraverseOpts o{prune, slack_rel, slack_ulps};
@@ -177,7 +216,12 @@ void emu_trace(void *h, const float *rays6, uint64_t n, int prune, float slack_r
 		Hit hit;
 		const FastRay fr = make_fast_ray(r, e->absmax);
 		const bool f = fast && fr.ok; // per ray here; the kernel votes per warp
-		if (anyhit && f)
+		const Node4 *n4 = e->nodes4.data();
+		if (wide && f && anyhit)
+			traverse<true, false, false, false, true, true>(e->nodes.data(), e->tris.data(), e->n, e->root, r, fr, o, hit, n4);
+		else if (wide && f)
+			traverse<false, true, true, true, true, true>(e->nodes.data(), e->tris.data(), e->n, e->root, r, fr, o, hit, n4);
+		else if (anyhit && f)
 			traverse<true, false, false, false, true>(e->nodes.data(), e->tris.data(), e->n, e->root, r, fr, o, hit);
 		else if (anyhit)
 			traverse<true, false, false, false, false>(e->nodes.data(), e->tris.data(), e->n, e->root, r, fr, o, hit);

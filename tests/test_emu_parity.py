@@ -156,3 +156,69 @@ def test_fast_box_test_is_conservative_and_changes_nothing(emu, oracle):
     assert np.array_equal(a["t"], b["t"]) and np.array_equal(a["pid"], b["pid"])
     oracle.build(tris)
     parity.assert_parity(parity.compare(oracle.trace(far), b, tris, far, oracle))
+
+
+def test_wide_quantised_nodes_are_conservative_and_change_nothing(emu, oracle):
+    """The compressed 4-wide nodes (8-bit boxes inside the node's bounds) are used only to skip
+    subtrees; every result field must equal the binary-node traversal, with and without pruning,
+    and -- unpruned -- every triangle the exact path tests must also be reached through the
+    quantised boxes (they may only be larger)."""
+    for name in ("blob_primary", "blob_incoherent", "soup_negative_t", "interior", "heightfield",
+                 "duplicates", "kat"):
+        tris, rays = CASES[name]
+        emu.build(tris, 13)
+        oracle.build(tris)
+        ref = oracle.trace(rays)
+        for prune in (0, 1):
+            binary = emu.trace(rays, prune=prune, fast=True, wide=False)
+            wide = emu.trace(rays, prune=prune, fast=True, wide=True)
+            for k in ("t", "u", "v", "pid", "valid", "px", "py", "pz"):
+                assert np.array_equal(binary[k], wide[k], equal_nan=True), (name, prune, k)
+            if prune == 0:
+                assert (wide["counts"][:, 1] >= binary["counts"][:, 1]).all()
+            # two binary levels per wide node: clearly fewer node fetches
+            if len(tris) > 100:
+                assert wide["counts"][:, 0].sum() < 0.8 * binary["counts"][:, 0].sum()
+        parity.assert_parity(parity.compare(ref, wide, tris, rays, oracle))
+    # far-away origins stress the margin of the quantised test as well
+    tris, rays = CASES["blob_primary"]
+    far = rays.copy()
+    far[:, 0:3] -= far[:, 3:6] * np.float32(5000.0)
+    emu.build(tris, 13)
+    a, b = emu.trace(far, wide=False), emu.trace(far, wide=True)
+    assert np.array_equal(a["t"], b["t"]) and np.array_equal(a["pid"], b["pid"])
+
+
+def test_wide_node_boxes_contain_their_children(emu):
+    """Dequantised child boxes of every wide node contain the exact child boxes (up to the
+    half-ulp saturation case the traversal margin covers)."""
+    tris = scenes.interior(5000)
+    emu.build(tris, 13)
+    nodes, _ = emu.download()
+    wide = emu.download_wide()
+    ch2 = nodes[:, 12:14].copy().view(np.int32)
+    for i in range(0, len(nodes), 7):
+        w = wide[i]
+        p = w[0:12].copy().view(np.float32)
+        scale = np.ldexp(1.0, w[12:15].astype(np.int64) - 127)
+        qlo = w[16:28].reshape(3, 4).astype(np.float64)
+        qhi = w[28:40].reshape(3, 4).astype(np.float64)
+        child = w[40:56].copy().view(np.int32)
+        # expected children: grandchildren (or the leaf child itself)
+        exp = []
+        for side in range(2):
+            c = ch2[i, side]
+            box = nodes[i, 6 * side:6 * side + 6]
+            if c >= 0:
+                exp.append((nodes[c, 0:6], ch2[c, 0]))
+                exp.append((nodes[c, 6:12], ch2[c, 1]))
+            else:
+                exp.append((box, c))
+        assert [int(c) for _, c in exp] == [int(c) for c in child[:len(exp)]]
+        assert all(int(c) == 0x7FFFFFFF for c in child[len(exp):])
+        for k, (box, _) in enumerate(exp):
+            lo = p + qlo[:, k] * scale
+            hi = p + qhi[:, k] * scale
+            tol = np.abs(box[3:6]).astype(np.float64) * 2.0 ** -23 + 1e-30
+            assert (lo <= box[0:3].astype(np.float64)).all()
+            assert (hi >= box[3:6].astype(np.float64) - tol).all()
