@@ -19,8 +19,14 @@ bunny-scale mesh, 1920x1080 coherent primary rays, all five filter tags (FullHit
   --impl reference  times only that CPU reference and prints the same line shape
 
 N > 1 (torchrun, one rank per GPU): rank 0's triangles are NCCL-broadcast, every rank builds the
-identical BVH, the ray batch is N x the single-GPU batch (weak scaling: N frames, rank r traces the
-r-th contiguous slice), hits stay in ray order and are NCCL-gathered to rank 0 in the e2e leg.
+identical BVH, the ray batch is N copies of the single-GPU batch (weak scaling; rank r traces the
+r-th contiguous slice, no collective on the data path).  In the e2e leg the whole batch lives in
+host shared memory, every rank DMA's its own page-locked slice through the host entry point and the
+hits land in ray order in the shared result.
+
+Other configs: --config c3 (262 k-tri interior, 4K primary), c3b (its one-bounce diffuse rays),
+c5 (1 M-tri height field, 8 M rays), c4 (10 M tris, 100 M incoherent rays; PRT_BENCH_C4_SPHERES /
+PRT_BENCH_C4_RAYS scale it down).
 """
 from __future__ import annotations
 
