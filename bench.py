@@ -258,7 +258,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_cpus = None
     if world > 1:
+        from portablert_b200 import sharding
+        if os.environ.get("PRT_BENCH_NUMA", "1") != "0":
+            numa_cpus = sharding.bind_near_gpu(local)  # host slices are first-touched GPU-locally
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -369,20 +373,20 @@ def main():
         e2e_pageable_s = (time.perf_counter() - t0) / e2e_steps
         api = "prt_b200_nearest_hits (pinned host rays -> pinned host HitReg AoS, 2-stream chunks)"
     else:
-        # The whole N-frame batch lives in host shared memory (rank 0 wrote it); every rank
-        # page-locks its own contiguous slice and calls the host entry point on it, so all PCIe
-        # links run in parallel and the hits land in ray order in the shared result buffer.
-        from portablert_b200 import sharding
+        # The whole N-frame batch lives in host shared memory; every rank page-locks its own
+        # contiguous slice (first-touched on its GPU's NUMA node) and calls the host entry point
+        # on it, so all PCIe links run in parallel and the hits land in ray order in the shared
+        # result buffer.  The synthetic batch is N copies of one frame: each rank writes its copy.
         tag = "prt_b200_%s" % os.environ.get("MASTER_PORT", "0")
         if rank == 0:
-            shm = sharding.SharedHostBatch(tag, total_rays, hitreg.dtype(mask), rank, world, True)
-            shm.rays[:n_rays] = rays
-            for r in range(1, world):
-                lo_r, hi_r = sharding.slice_bounds(total_rays, world, r)
-                shm.rays[lo_r:hi_r] = rays
+            shm = sharding.SharedHostBatch(tag, total_rays, hitreg.dtype(mask), rank, world, True,
+                                           first_touch=True)
         barrier()
         if rank != 0:
-            shm = sharding.SharedHostBatch(tag, total_rays, hitreg.dtype(mask), rank, world, False)
+            shm = sharding.SharedHostBatch(tag, total_rays, hitreg.dtype(mask), rank, world, False,
+                                           first_touch=True)
+        shm.my_rays[:] = rays
+        barrier()
 
         def e2e_step():
             backend.nearest_hits(shm.my_rays, mask, out=shm.my_hits)
@@ -492,7 +496,10 @@ def main():
                    "multi_gpu": "tris NCCL-broadcast from rank 0, identical BVH built on every rank, "
                                 "batch = N copies of the workload's rays, rank r traces the r-th contiguous slice; e2e: "
                                 "batch in host shared memory, each rank DMA's its own slice, hits "
-                                "land in ray order in the shared result"},
+                                "land in ray order in the shared result",
+                   "numa": (None if world == 1 else
+                            "rank pinned to %d GPU-local CPUs, slices first-touched there"
+                            % len(numa_cpus) if numa_cpus else "no NUMA binding")},
         "build_mtris_s": build["mtris_s"], "build": build,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline, "cpu_baseline": cpu,

@@ -28,6 +28,32 @@ def _dist():
     return dist
 
 
+def bind_near_gpu(device_index: int):
+    """Pin this process (and the threads it starts later) to the CPUs NVML reports as local to
+    the GPU, so that the pages this rank touches first -- its slice of a SharedHostBatch -- are
+    allocated on the NUMA node its PCIe link hangs off.  Without it a host batch written by one
+    process sits on one socket and the GPUs of the other socket DMA across the inter-socket link.
+    Placement only: returns the CPU list, or None when NVML or the cpuset do not allow it."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:  # NVML numbers the physical devices
+            device_index = int(vis.split(",")[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, x in enumerate(words) for b in range(64) if (int(x) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def broadcast_scene(tris, device, src: int = 0, group=None):
     """Rank `src` passes its (N,9) float32 triangles, the others pass None; everyone gets a tensor
     on `device` (36*N bytes over NVLink with NCCL)."""
@@ -125,7 +151,11 @@ class SharedHostBatch:
     and the hits land in ray order in the shared result -- no funnel through rank 0, no collective
     on the data path.  (The NCCL scatter/gather above is for batches that live on a GPU.)"""
 
-    def __init__(self, name: str, n_rays: int, hit_dtype, rank: int, world: int, create: bool):
+    def __init__(self, name: str, n_rays: int, hit_dtype, rank: int, world: int, create: bool,
+                 first_touch: bool = False):
+        """first_touch=True zero-fills this rank's slices so that their pages are allocated on the
+        NUMA node the rank runs on (see bind_near_gpu).  Only for a batch nobody has written yet:
+        construct on every rank, synchronise, then fill."""
         import ctypes as C
 
         from ._lib import lib
@@ -135,6 +165,9 @@ class SharedHostBatch:
         self.rays = np.memmap(self.paths[0], np.float32, mode, shape=(n_rays, 6))
         self.hits = np.memmap(self.paths[1], np.dtype(hit_dtype), mode, shape=(n_rays,))
         self.lo, self.hi = slice_bounds(n_rays, world, rank)
+        if first_touch:
+            self.rays[self.lo:self.hi] = 0
+            self.hits[self.lo:self.hi] = np.zeros((), np.dtype(hit_dtype))
         self._reg = []
         page = 4096
         for arr, item in ((self.rays, 24), (self.hits, np.dtype(hit_dtype).itemsize)):
