@@ -371,7 +371,26 @@ def main():
         for _ in range(e2e_steps):
             hits = backend.nearest_hits(rays, mask)
         e2e_pageable_s = (time.perf_counter() - t0) / e2e_steps
-        api = "prt_b200_nearest_hits (pinned host rays -> pinned host HitReg AoS, 2-stream chunks)"
+        api = "prt_b200_nearest_hits (pinned host rays -> pinned host HitReg AoS; H2D, traversal and D2H pipelined over chunks)"
+        # the PCIe floor of that call on this box: both directions run concurrently, so the call
+        # cannot beat max(H2D bytes / H2D bandwidth, D2H bytes / D2H bandwidth)
+        raw_in = torch.from_numpy(p_rays.view(np.uint8).reshape(-1))
+        raw_out = torch.from_numpy(p_hits.view(np.uint8).reshape(-1))
+        d_in = torch.empty(raw_in.numel(), dtype=torch.uint8, device=dev)
+        d_out = torch.empty(raw_out.numel(), dtype=torch.uint8, device=dev)
+        pcie = {}
+        for name, dst, src in (("h2d", d_in, raw_in), ("d2h", raw_out, d_out)):
+            best = float("inf")
+            for _ in range(5):
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                dst.copy_(src, non_blocking=True)
+                ev1.record()
+                torch.cuda.synchronize()
+                best = min(best, ev0.elapsed_time(ev1))
+            pcie[name + "_gbs"] = src.numel() / best / 1e6
+            pcie[name + "_ms"] = best
+        pcie["floor_ms"] = max(pcie["h2d_ms"], pcie["d2h_ms"])
     else:
         # The whole N-frame batch lives in host shared memory; every rank page-locks its own
         # contiguous slice (first-touched on its GPU's NUMA node) and calls the host entry point
@@ -412,6 +431,8 @@ def main():
            "h2d_bytes_per_step": 24 * total_rays, "d2h_bytes_per_step": stride * total_rays,
            "ms_per_step": e2e_s * 1e3, "api": api}
     if world == 1:
+        e2e["pcie"] = pcie
+        e2e["frac_of_pcie_floor"] = pcie["floor_ms"] / (e2e_s * 1e3)
         e2e["pageable_value"] = total_rays / e2e_pageable_s / 1e6
         e2e["pageable_note"] = ("same call with pageable numpy input and a freshly allocated "
                                 "result (staged through pinned buffers by threaded memcpy)")

@@ -2,7 +2,9 @@
 // grow-only device scratch, pinned double-buffered staging for the host-pointer entry points, CUDA
 // event timing.  No computation happens on the host and there is no CPU fallback.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -77,21 +79,25 @@ int prt_b200_create(prt_b200 **out, int device) {
 		e = cudaGetDeviceProperties(&prop, device);
 	if (e == cudaSuccess)
 		e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-	for (int k = 0; k < 2 && e == cudaSuccess; ++k)
-		e = cudaStreamCreateWithFlags(&c->copy_stream[k], cudaStreamNonBlocking);
+	for (int k = 0; k < 3 && e == cudaSuccess; ++k)
+		e = cudaStreamCreateWithFlags(&c->pipe_stream[k], cudaStreamNonBlocking);
 	if (e == cudaSuccess)
 		e = cudaEventCreate(&c->ev0);
 	if (e == cudaSuccess)
 		e = cudaEventCreate(&c->ev1);
-	for (int k = 0; k < 2 && e == cudaSuccess; ++k)
-		for (int j = 0; j < 2 && e == cudaSuccess; ++j)
-			e = cudaEventCreateWithFlags(&c->ev_chunk[k][j], cudaEventDisableTiming);
+	for (int k = 0; k < prt_b200::PIPE && e == cudaSuccess; ++k)
+		for (int j = 0; j < 3 && e == cudaSuccess; ++j)
+			e = cudaEventCreateWithFlags(&c->ev_pipe[k][j], cudaEventDisableTiming);
 	if (e == cudaSuccess)
 		e = cudaHostAlloc(reinterpret_cast<void **>(&c->probe_host), 64, cudaHostAllocMapped);
 	if (e == cudaSuccess)
 		e = cudaHostGetDevicePointer(reinterpret_cast<void **>(&c->probe_dev), c->probe_host, 0);
 	if (e == cudaSuccess)
 		e = c->probe_ticket.reserve(64);
+	if (e == cudaSuccess)
+		e = c->counter.reserve(256);
+	if (e == cudaSuccess)
+		e = cudaMemset(c->counter.p, 0, 256); // the traversal kernel re-arms its counters itself
 	if (e != cudaSuccess) {
 		g_create_err = std::string("create: ") + cudaGetErrorString(e);
 		prt_b200_destroy(c);
@@ -104,6 +110,10 @@ int prt_b200_create(prt_b200 **out, int device) {
 		c->wide_mode = std::max(0, std::min(2, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_SORT_RAYS"))
 		c->sort_rays = std::max(0, std::min(2, std::atoi(e)));
+	if (const char *e = std::getenv("PRT_B200_PIPE_TRACE"))
+		c->pipe_trace = std::atoi(e) != 0;
+	if (const char *e = std::getenv("PRT_B200_CHUNK_LOG2"))
+		c->chunk_log2 = std::max(10, std::min(19, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_REFILL"))
 		c->refill = std::max(0, std::min(32, std::atoi(e)));
 	c->name = prop.name;
@@ -121,7 +131,6 @@ void prt_b200_destroy(prt_b200 *c) {
 	prt::DevBuf *bufs[] = {&c->tris_raw, &c->nodes,    &c->trirecs,     &c->nodes4,     &c->keys[0],     &c->keys[1],
 	                       &c->vals[0],  &c->vals[1],  &c->sort_scratch, &c->bounds,
 	                       &c->leaf_box, &c->bound,    &c->root_info,
-	                       &c->rays_dev[0], &c->rays_dev[1], &c->hits_dev[0], &c->hits_dev[1],
 	                       &c->counter};
 	for (auto *b : bufs)
 		b->release();
@@ -135,15 +144,18 @@ void prt_b200_destroy(prt_b200 *c) {
 		r.vals[1].release();
 		r.scratch.release();
 	}
-	for (int k = 0; k < 2; ++k) {
+	for (int k = 0; k < prt_b200::PIPE; ++k) {
+		c->rays_dev[k].release();
+		c->hits_dev[k].release();
 		c->rays_pin[k].release();
 		c->hits_pin[k].release();
-		if (c->copy_stream[k])
-			cudaStreamDestroy(c->copy_stream[k]);
-		for (int j = 0; j < 2; ++j)
-			if (c->ev_chunk[k][j])
-				cudaEventDestroy(c->ev_chunk[k][j]);
+		for (int j = 0; j < 3; ++j)
+			if (c->ev_pipe[k][j])
+				cudaEventDestroy(c->ev_pipe[k][j]);
 	}
+	for (int k = 0; k < 3; ++k)
+		if (c->pipe_stream[k])
+			cudaStreamDestroy(c->pipe_stream[k]);
 	if (c->ev0)
 		cudaEventDestroy(c->ev0);
 	if (c->ev1)
@@ -342,9 +354,9 @@ static void par_memcpy(void *dst, const void *src, size_t bytes) {
 		t.join();
 }
 
-// Rays are cut into chunks; chunk k runs on stream k&1: H2D -> traversal kernel writing the
-// caller's AoS records -> D2H, so the copies of one chunk overlap the traversal of the other.
-// Pageable host memory (a std::vector) is staged through pinned buffers with a threaded memcpy;
+// Rays are cut into chunks that flow through three stages on three streams -- H2D, traversal kernel
+// writing the caller's AoS records, D2H -- over a ring of buffer sets, so both copy engines and
+// the SMs work at the same time.  Pageable host memory (a std::vector) is staged through pinned buffers with a threaded memcpy;
 // pinned / registered host memory is DMA'd directly.
 int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t mask,
                           const prt_hit_layout *layout, void *hits_out) {
@@ -359,9 +371,33 @@ int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t 
 	PRT_CUDA(c, cudaSetDevice(c->device));
 
 	const bool in_pinned = is_pinned(rays6), out_pinned = is_pinned(hits_out);
-	const uint64_t CH = std::min<uint64_t>(n, 1ull << 19);
+	// Chunk schedule: the D2H engine is the bottleneck (records are larger than rays) and starts
+	// only when the first chunk has been uploaded and traced, so small batches are cut into ~8
+	// chunks; every chunk costs launches, a shorter (less efficient) kernel and some idle time of
+	// the copy engines between transfers, so not more.  Chunks are multiples of 2^16 rays (the
+	// reordering threshold) and at most 2^19.  Measured on C2 (2 073 600 rays, pinned buffers,
+	// wall clock per call): 2^16 1.94 ms, 2^17 1.65, 2^18 1.60, n/6 1.69, 2^19 1.72; a small first
+	// chunk followed by doubling ones was slower (the uploads fall behind the downloads), and so
+	// were kernels that read rays / write records through PCIe themselves (2.07 / 9.7 ms).
+	// PRT_B200_CHUNK_LOG2 forces a size.
+	uint64_t CH = ((n + 7) / 8 + 65535) / 65536 * 65536;
+	if (c->chunk_log2 > 0)
+		CH = 1ull << c->chunk_log2;
+	CH = std::min<uint64_t>(std::min<uint64_t>(CH, 1ull << 19), n);
+	std::vector<uint64_t> start; // chunk k = rays [start[k], start[k+1])
+	for (uint64_t at = 0; at < n; at += CH)
+		start.push_back(at);
+	start.push_back(n);
+	// coherent or not is decided once, on the host copy of the batch (no device probe, no stream
+	// synchronisation inside the pipeline)
+	const auto call0 = std::chrono::steady_clock::now();
+	const int coherence = (c->sort_rays == 2 && n >= 65536) ? prt::host_ray_probe(c, rays6, n) : -1;
+	const double probe_us =
+	    std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - call0).count();
+	constexpr int PIPE = prt_b200::PIPE;
 	const size_t ray_b = 24, hit_b = layout->stride;
-	for (int k = 0; k < 2; ++k) {
+	const uint64_t n_chunks = start.size() - 1;
+	for (int k = 0; k < PIPE && (uint64_t)k < n_chunks; ++k) {
 		PRT_CUDA(c, c->rays_dev[k].reserve(CH * ray_b));
 		PRT_CUDA(c, c->hits_dev[k].reserve(CH * hit_b));
 		if (!in_pinned)
@@ -369,54 +405,122 @@ int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t 
 		if (!out_pinned)
 			PRT_CUDA(c, c->hits_pin[k].reserve(CH * hit_b));
 	}
-	const uint64_t n_chunks = (n + CH - 1) / CH;
+	enum { IN = 0, KERN = 1, OUT = 2 };
+	cudaStream_t s_in = c->pipe_stream[IN], s_k = c->pipe_stream[KERN], s_out = c->pipe_stream[OUT];
 	auto drain = [&](uint64_t k) -> cudaError_t { // chunk k's D2H is done: hand the records over
-		const int b = (int)(k & 1);
-		cudaError_t e = cudaEventSynchronize(c->ev_chunk[b][1]);
-		if (e == cudaSuccess && !out_pinned) {
-			const uint64_t pf = k * CH, pc = std::min(CH, n - pf);
+		const int b = (int)(k % PIPE);
+		cudaError_t e = cudaEventSynchronize(c->ev_pipe[b][OUT]);
+		if (e == cudaSuccess) {
+			const uint64_t pf = start[k], pc = start[k + 1] - pf;
 			par_memcpy(static_cast<char *>(hits_out) + pf * hit_b, c->hits_pin[b].p, pc * hit_b);
 		}
 		return e;
 	};
-	// the context stream marks the start; both chunk streams wait for it (the BVH build ran there)
+	// Three stages on three streams over a ring of PIPE buffer sets: the H2D engine, the SMs and
+	// the D2H engine each run back to back; a stage waits only for the event that frees what it
+	// needs (the previous stage of the same chunk, the next stage of the chunk PIPE earlier).
+	// The context stream marks the start (the BVH build ran there).
 	PRT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-	for (int k = 0; k < 2; ++k)
-		PRT_CUDA(c, cudaStreamWaitEvent(c->copy_stream[k], c->ev0, 0));
+	for (int k = 0; k < 3; ++k)
+		PRT_CUDA(c, cudaStreamWaitEvent(c->pipe_stream[k], c->ev0, 0));
+	uint64_t drained = 0; // pageable results: chunks [0, drained) are in the caller's array
+	// PRT_B200_PIPE_TRACE=1: device timeline of every stage of every chunk, printed to stderr
+	std::vector<cudaEvent_t> tl;
+	std::vector<double> host_us;
+	const auto wall0 = std::chrono::steady_clock::now();
+	auto mark = [&](cudaStream_t st) {
+		if (!c->pipe_trace)
+			return;
+		cudaEvent_t e;
+		cudaEventCreate(&e);
+		cudaEventRecord(e, st);
+		tl.push_back(e);
+	};
 	for (uint64_t k = 0; k < n_chunks; ++k) {
-		const int b = (int)(k & 1);
-		cudaStream_t s = c->copy_stream[b];
-		const uint64_t first = k * CH, cnt = std::min(CH, n - first);
-		if (k >= 2)
-			PRT_CUDA(c, drain(k - 2)); // buffer set b is free again
+		const int b = (int)(k % PIPE);
+		const uint64_t first = start[k], cnt = start[k + 1] - first;
+		// ---- H2D
 		const void *src = rays6 + first * 6;
 		if (!in_pinned) {
+			if (k >= (uint64_t)PIPE) // staging buffer b: its previous H2D must have left
+				PRT_CUDA(c, cudaEventSynchronize(c->ev_pipe[b][IN]));
 			par_memcpy(c->rays_pin[b].p, src, cnt * ray_b);
 			src = c->rays_pin[b].p;
 		}
-		PRT_CUDA(c, cudaMemcpyAsync(c->rays_dev[b].p, src, cnt * ray_b, cudaMemcpyHostToDevice, s));
+		if (k >= (uint64_t)PIPE) // device rays b: the kernel of chunk k-PIPE must have left
+			PRT_CUDA(c, cudaStreamWaitEvent(s_in, c->ev_pipe[b][KERN], 0));
+		if (c->pipe_trace)
+			host_us.push_back(std::chrono::duration<double, std::micro>(
+			                      std::chrono::steady_clock::now() - wall0).count());
+		mark(s_in);
+		PRT_CUDA(c, cudaMemcpyAsync(c->rays_dev[b].p, src, cnt * ray_b, cudaMemcpyHostToDevice, s_in));
+		mark(s_in);
+		PRT_CUDA(c, cudaEventRecord(c->ev_pipe[b][IN], s_in));
+		// ---- traversal (all chunks on one stream: one counter / reordering scratch slot)
+		PRT_CUDA(c, cudaStreamWaitEvent(s_k, c->ev_pipe[b][IN], 0));
+		if (k >= (uint64_t)PIPE) // device hits b: the D2H of chunk k-PIPE must have left
+			PRT_CUDA(c, cudaStreamWaitEvent(s_k, c->ev_pipe[b][OUT], 0));
 		prt::TraceOut out;
 		out.aos = c->hits_dev[b].p;
 		out.layout = *layout;
-		out.slot = b;
-		int rc = prt::launch_trace(c, c->rays_dev[b].as<float>(), cnt, mask, out, nullptr, s);
+		out.slot = 0;
+		mark(s_k);
+		int rc = prt::launch_trace(c, c->rays_dev[b].as<float>(), cnt, mask, out, nullptr, s_k,
+		                           coherence);
 		if (rc)
 			return rc;
+		mark(s_k);
+		PRT_CUDA(c, cudaEventRecord(c->ev_pipe[b][KERN], s_k));
+		// ---- D2H
+		if (!out_pinned && k >= (uint64_t)PIPE) { // staging buffer b still holds chunk k-PIPE
+			for (; drained <= k - PIPE; ++drained)
+				PRT_CUDA(c, drain(drained));
+		}
+		PRT_CUDA(c, cudaStreamWaitEvent(s_out, c->ev_pipe[b][KERN], 0));
 		void *dst = out_pinned ? static_cast<void *>(static_cast<char *>(hits_out) + first * hit_b)
 		                       : c->hits_pin[b].p;
-		PRT_CUDA(c, cudaMemcpyAsync(dst, c->hits_dev[b].p, cnt * hit_b, cudaMemcpyDeviceToHost, s));
-		PRT_CUDA(c, cudaEventRecord(c->ev_chunk[b][1], s));
+		mark(s_out);
+		PRT_CUDA(c, cudaMemcpyAsync(dst, c->hits_dev[b].p, cnt * hit_b, cudaMemcpyDeviceToHost, s_out));
+		mark(s_out);
+		PRT_CUDA(c, cudaEventRecord(c->ev_pipe[b][OUT], s_out));
+		// pageable results: copy out whatever has already arrived, without waiting for it
+		if (!out_pinned)
+			while (drained < k) {
+				if (cudaEventQuery(c->ev_pipe[drained % PIPE][OUT]) != cudaSuccess) {
+					cudaGetLastError(); // "not ready" is not an error
+					break;
+				}
+				PRT_CUDA(c, drain(drained));
+				++drained;
+			}
 	}
-	for (uint64_t k = n_chunks >= 2 ? n_chunks - 2 : 0; k < n_chunks; ++k)
-		PRT_CUDA(c, drain(k));
-	// join the chunk streams back into the context stream and time the whole call on the device
-	for (int k = 0; k < 2; ++k) {
-		PRT_CUDA(c, cudaEventRecord(c->ev_chunk[k][0], c->copy_stream[k]));
-		PRT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_chunk[k][0], 0));
-	}
+	if (!out_pinned)
+		for (; drained < n_chunks; ++drained)
+			PRT_CUDA(c, drain(drained));
+	// the last D2H depends on everything before it: join it into the context stream and time the
+	// whole call on the device
+	PRT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_pipe[(n_chunks - 1) % PIPE][OUT], 0));
 	PRT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
 	PRT_CUDA(c, cudaStreamSynchronize(c->stream));
 	PRT_CUDA(c, cudaEventElapsedTime(&c->last_trace_ms, c->ev0, c->ev1));
+	if (c->pipe_trace) {
+		std::fprintf(stderr, "[prt_b200] nearest_hits %llu rays, %llu chunks of %llu, device %.3f ms, "
+		                     "host probe %.0f us, call %.0f us "
+		                     "(chunk: enqueue us | h2d | kernel | d2h, ms since start)\n",
+		             (unsigned long long)n, (unsigned long long)n_chunks, (unsigned long long)CH,
+		             c->last_trace_ms, probe_us,
+		             std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - call0)
+		                 .count());
+		for (uint64_t k = 0; k < n_chunks; ++k) {
+			float t[6];
+			for (int j = 0; j < 6; ++j)
+				cudaEventElapsedTime(&t[j], c->ev0, tl[k * 6 + j]);
+			std::fprintf(stderr, "  %3llu: %7.1f | %.3f-%.3f | %.3f-%.3f | %.3f-%.3f\n",
+			             (unsigned long long)k, host_us[k], t[0], t[1], t[2], t[3], t[4], t[5]);
+		}
+		for (cudaEvent_t e : tl)
+			cudaEventDestroy(e);
+	}
 	return PRT_OK;
 }
 

@@ -69,9 +69,12 @@ struct prt_b200 {
 	int device = -1;
 	int sm_count = 0;
 	cudaStream_t stream = nullptr;
-	cudaStream_t copy_stream[2] = {nullptr, nullptr};
+	// host entry point: one stream per pipeline stage (H2D, kernels, D2H) over a ring of
+	// PIPE chunk buffers; ev_pipe[b][stage] = "that stage has left buffer set b"
+	static constexpr int PIPE = 4;
+	cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-	cudaEvent_t ev_chunk[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+	cudaEvent_t ev_pipe[PIPE][3] = {};
 	std::string name;
 	std::string err;
 
@@ -89,8 +92,8 @@ struct prt_b200 {
 	int32_t root = 0; // index of the root node (the radix tree numbers nodes by split position)
 
 	// trace scratch
-	prt::DevBuf rays_dev[2], hits_dev[2], counter;
-	// ray reordering scratch, one set per launch slot (the host entry point runs two streams)
+	prt::DevBuf rays_dev[PIPE], hits_dev[PIPE], counter;
+	// ray reordering scratch, one set per launch slot (concurrent launches on different streams)
 	struct RaySort {
 		prt::DevBuf keys[2], vals[2], scratch;
 	} rs[2];
@@ -101,13 +104,15 @@ struct prt_b200 {
 	float scene_lo[3] = {0.f, 0.f, 0.f}, scene_hi[3] = {0.f, 0.f, 0.f};
 	uint64_t sorted_batches = 0, unsorted_batches = 0, wide_batches = 0;
 	bool wide_built = false, last_wide = false;
-	prt::PinnedBuf rays_pin[2], hits_pin[2];
+	prt::PinnedBuf rays_pin[PIPE], hits_pin[PIPE];
 
 	prt_trace_opts opts{1, 1e-4f, 64.0f};
 
 	float scene_absmax[3] = {0.f, 0.f, 0.f}; // largest |coordinate| per axis (fast box-test margin)
 	int fast_boxes = 1;                      // env PRT_B200_FAST_BOXES=0 forces the exact test everywhere
 	int refill = 16;                         // env PRT_B200_REFILL: dynamic ray-fetch threshold (lanes)
+	int chunk_log2 = 0; // host entry point: rays per pipeline chunk (0 = automatic)
+	bool pipe_trace = false; // env PRT_B200_PIPE_TRACE: print the stage timeline of every host call
 	uint64_t launches = 0;
 	float last_build_ms = 0.f, last_trace_ms = 0.f;
 };
@@ -143,8 +148,11 @@ struct TraceOut {
 	prt_hit_layout layout{};
 	int slot = 0; // which ray counter to use (concurrent launches on different streams)
 };
+// coherence: -1 = probe the batch on the device (one stream synchronisation), 0 = known coherent,
+// 1 = known incoherent (reorder it)
 int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, const TraceOut &out,
-                 uint32_t *d_counts, cudaStream_t stream);
+                 uint32_t *d_counts, cudaStream_t stream, int coherence = -1);
+int host_ray_probe(const prt_b200 *c, const float *rays6, uint64_t n);
 
 // sort.cu
 int radix_sort_pairs(prt_b200 *c, DevBuf &scratch, uint64_t *const keys[2], uint32_t *const vals[2],

@@ -58,24 +58,36 @@ struct TraceParams {
 // so the output order is unchanged.  Measured x1.39 (10 M tris / random rays) and x1.45 (one-bounce
 // diffuse rays in the 262 k-tri interior); coherent primary rays gain nothing, which the key
 // kernel detects (most neighbouring rays already share their key) so that the sort is skipped.
-__device__ __forceinline__ uint32_t spread4(uint32_t v) { // 4 bits -> every third bit
+__host__ __device__ __forceinline__ uint32_t spread4(uint32_t v) { // 4 bits -> every third bit
 	return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6);
 }
 
-__device__ __forceinline__ uint32_t ray_key(const float *__restrict__ r, float3 lo, float3 inv_ext) {
-	const float ox = __ldg(r), oy = __ldg(r + 1), oz = __ldg(r + 2);
-	const float dx = __ldg(r + 3), dy = __ldg(r + 4), dz = __ldg(r + 5);
-	const float inv = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-37f));
+__host__ __device__ __forceinline__ uint32_t ray_key_of(float ox, float oy, float oz, float dx, float dy,
+                                                        float dz, float3 lo, float3 inv_ext) {
 	// NaN / out-of-box values clamp into the grid; the key only steers the processing order
-	const uint32_t qx = (uint32_t)fminf(fmaxf((ox - lo.x) * inv_ext.x * 16.f, 0.f), 15.f);
-	const uint32_t qy = (uint32_t)fminf(fmaxf((oy - lo.y) * inv_ext.y * 16.f, 0.f), 15.f);
-	const uint32_t qz = (uint32_t)fminf(fmaxf((oz - lo.z) * inv_ext.z * 16.f, 0.f), 15.f);
-	const uint32_t ux = (uint32_t)fminf(fmaxf((dx * inv * 0.5f + 0.5f) * 16.f, 0.f), 15.f);
-	const uint32_t uy = (uint32_t)fminf(fmaxf((dy * inv * 0.5f + 0.5f) * 16.f, 0.f), 15.f);
-	const uint32_t uz = (uint32_t)fminf(fmaxf((dz * inv * 0.5f + 0.5f) * 16.f, 0.f), 15.f);
+#if defined(__CUDA_ARCH__)
+	const float inv = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-37f));
+#define PRT_Q16(x) ((uint32_t)fminf(fmaxf((x), 0.f), 15.f))
+#else
+	const float d2 = dx * dx + dy * dy + dz * dz;
+	const float inv = 1.0f / sqrtf(d2 > 1e-37f ? d2 : 1e-37f);
+#define PRT_Q16(x) (!((x) > 0.f) ? 0u : ((x) >= 15.f ? 15u : (uint32_t)(x)))
+#endif
+	const uint32_t qx = PRT_Q16((ox - lo.x) * inv_ext.x * 16.f);
+	const uint32_t qy = PRT_Q16((oy - lo.y) * inv_ext.y * 16.f);
+	const uint32_t qz = PRT_Q16((oz - lo.z) * inv_ext.z * 16.f);
+	const uint32_t ux = PRT_Q16((dx * inv * 0.5f + 0.5f) * 16.f);
+	const uint32_t uy = PRT_Q16((dy * inv * 0.5f + 0.5f) * 16.f);
+	const uint32_t uz = PRT_Q16((dz * inv * 0.5f + 0.5f) * 16.f);
+#undef PRT_Q16
 	const uint32_t mo = (spread4(qx) << 2) | (spread4(qy) << 1) | spread4(qz);
 	const uint32_t md = (spread4(ux) << 2) | (spread4(uy) << 1) | spread4(uz);
 	return (mo << 12) | md;
+}
+
+__device__ __forceinline__ uint32_t ray_key(const float *__restrict__ r, float3 lo, float3 inv_ext) {
+	return ray_key_of(__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3), __ldg(r + 4), __ldg(r + 5),
+	                  lo, inv_ext);
 }
 
 __global__ void __launch_bounds__(256)
@@ -254,6 +266,16 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceParams P) {
 		}
 		__syncwarp();
 	}
+	// The last warp to leave re-arms the counters for the next launch (no cudaMemset between
+	// launches: inside the host pipeline a 16-byte memset queues behind megabytes of DMA).  A warp
+	// gets here only after its last fetch, so nobody touches the ray counter any more.
+	if (lane == 0) {
+		const unsigned long long warps = (unsigned long long)gridDim.x * (TRACE_THREADS / 32);
+		if (atomicAdd(P.counter + 2, 1ull) == warps - 1) {
+			P.counter[0] = 0;
+			P.counter[2] = 0;
+		}
+	}
 }
 
 using KernelFn = void (*)(const TraceParams);
@@ -275,8 +297,39 @@ static KernelFn g_table[32][4];
 static int g_blocks_per_sm[32][4];
 static bool g_table_ready = false;
 
+static void scene_grid(const prt_b200 *c, float3 &lo, float3 &ie) {
+	lo = make_float3(c->scene_lo[0], c->scene_lo[1], c->scene_lo[2]);
+	ie.x = c->scene_hi[0] > c->scene_lo[0] ? 1.f / (c->scene_hi[0] - c->scene_lo[0]) : 0.f;
+	ie.y = c->scene_hi[1] > c->scene_lo[1] ? 1.f / (c->scene_hi[1] - c->scene_lo[1]) : 0.f;
+	ie.z = c->scene_hi[2] > c->scene_lo[2] ? 1.f / (c->scene_hi[2] - c->scene_lo[2]) : 0.f;
+}
+
+// The coherence probe of k_ray_probe on a batch that still lives in HOST memory (same sampled
+// statistic on fewer segments): the host entry point decides once per call, so that its chunk
+// pipeline never waits for a device-side probe.  1 = incoherent (reorder), 0 = coherent.
+int host_ray_probe(const prt_b200 *c, const float *rays6, uint64_t n) {
+	float3 lo, ie;
+	scene_grid(c, lo, ie);
+	constexpr uint64_t HOST_SEGS = 64; // a quarter of the device probe's sample: ~20 us of host time
+	const uint64_t n_seg = n / 32;
+	const uint64_t segs = std::min<uint64_t>(HOST_SEGS, n_seg);
+	uint64_t same = 0;
+	for (uint64_t w = 0; w < segs; ++w) {
+		const uint64_t seg = n_seg >= HOST_SEGS ? w * (n_seg / HOST_SEGS) : w;
+		const float *r = rays6 + seg * 32 * 6;
+		uint32_t prev = ray_key_of(r[0], r[1], r[2], r[3], r[4], r[5], lo, ie);
+		for (int l = 1; l < 32; ++l) {
+			r += 6;
+			const uint32_t k = ray_key_of(r[0], r[1], r[2], r[3], r[4], r[5], lo, ie);
+			same += (k == prev);
+			prev = k;
+		}
+	}
+	return same * 2 < segs * 31 ? 1 : 0;
+}
+
 int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, const TraceOut &out,
-                 uint32_t *d_counts, cudaStream_t s) {
+                 uint32_t *d_counts, cudaStream_t s, int coherence) {
 	if (mask == 0 || mask > PRT_TAG_ALL)
 		return fail(c, PRT_E_ARG, "nearest_hits: tag mask must be in 1..31");
 	if (n == 0)
@@ -311,9 +364,9 @@ int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, c
 		P.scene_absmax[a] = c->scene_absmax[a];
 	P.fast = c->fast_boxes;
 	P.refill = c->refill;
-	PRT_CUDA(c, c->counter.reserve(256));
-	P.counter = c->counter.as<unsigned long long>() + 2 * out.slot; // 16 bytes apart
-	PRT_CUDA(c, cudaMemsetAsync(P.counter, 0, 16, s));               // ray counter + coherence probe
+	// [0] ray counter, [1] coherence-probe count, [2] warps that left: zeroed at create, re-armed by
+	// the kernel itself (32 bytes per launch slot)
+	P.counter = c->counter.as<unsigned long long>() + 4 * out.slot;
 
 	// ---- optional ray reordering (see k_ray_keys)
 	P.perm = nullptr;
@@ -323,13 +376,12 @@ int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, c
 			PRT_CUDA(c, rs.keys[k].reserve(n * 8));
 			PRT_CUDA(c, rs.vals[k].reserve(n * 4));
 		}
-		float3 lo = make_float3(c->scene_lo[0], c->scene_lo[1], c->scene_lo[2]);
-		float3 ie;
-		ie.x = c->scene_hi[0] > c->scene_lo[0] ? 1.f / (c->scene_hi[0] - c->scene_lo[0]) : 0.f;
-		ie.y = c->scene_hi[1] > c->scene_lo[1] ? 1.f / (c->scene_hi[1] - c->scene_lo[1]) : 0.f;
-		ie.z = c->scene_hi[2] > c->scene_lo[2] ? 1.f / (c->scene_hi[2] - c->scene_lo[2]) : 0.f;
+		float3 lo, ie;
+		scene_grid(c, lo, ie);
 		bool do_sort = true;
-		if (c->sort_rays == 2) { // auto: skip batches that are already coherent
+		if (c->sort_rays == 2 && coherence >= 0) { // the caller probed the batch on the host
+			do_sort = coherence != 0;
+		} else if (c->sort_rays == 2) { // auto: skip batches that are already coherent
 			volatile unsigned long long *flag = c->probe_host + out.slot;
 			*flag = 0;
 			PRT_CUDA(c, cudaMemsetAsync(P.counter + 1, 0, 8, s));
