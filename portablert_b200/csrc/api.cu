@@ -6,13 +6,48 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <vector>
 
 #include "prt_ctx.h"
 
 using prt::fail;
+
+namespace {
+// Hand-offs between the thread that enqueues the pipeline of the host entry point and the two
+// threads that stage pageable caller memory through pinned buffers (see prt_b200_nearest_hits).
+struct Progress {
+	std::mutex m;
+	std::condition_variable cv;
+	uint64_t produced = 0; // chunks whose rays are in their staging buffer
+	uint64_t issued = 0;   // chunks whose copies and kernel have been enqueued (events recorded)
+	uint64_t consumed = 0; // chunks whose records have reached the caller's array
+	bool stop = false;     // error or early return: everybody leaves
+	cudaError_t err = cudaSuccess;
+	template <class F> bool wait(F ok) {
+		std::unique_lock<std::mutex> l(m);
+		cv.wait(l, [&] { return stop || ok(); });
+		return !stop;
+	}
+	template <class F> void post(F f) {
+		{
+			std::lock_guard<std::mutex> l(m);
+			f();
+		}
+		cv.notify_all();
+	}
+	void fail(cudaError_t e) {
+		post([&] {
+			if (err == cudaSuccess)
+				err = e;
+			stop = true;
+		});
+	}
+};
+} // namespace
 
 static thread_local std::string g_create_err;
 
@@ -332,8 +367,13 @@ static bool is_pinned(const void *p) {
 // the PCIe transfer and the traversal together
 static void par_memcpy(void *dst, const void *src, size_t bytes) {
 	const size_t MIN_PER_THREAD = 2u << 20;
+	static const int max_threads = [] {
+		const char *e = std::getenv("PRT_B200_COPY_THREADS");
+		return e ? std::max(1, std::min(32, std::atoi(e))) : 8;
+	}();
 	unsigned hw = std::thread::hardware_concurrency();
-	size_t nt = std::min<size_t>(std::min<size_t>(hw ? hw : 1, 8), bytes / MIN_PER_THREAD);
+	size_t nt = std::min<size_t>(std::min<size_t>(hw ? hw : 1, (size_t)max_threads),
+	                             bytes / MIN_PER_THREAD);
 	if (nt <= 1) {
 		std::memcpy(dst, src, bytes);
 		return;
@@ -381,6 +421,8 @@ int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t 
 	// were kernels that read rays / write records through PCIe themselves (2.07 / 9.7 ms).
 	// PRT_B200_CHUNK_LOG2 forces a size.
 	uint64_t CH = ((n + 7) / 8 + 65535) / 65536 * 65536;
+	if (!in_pinned || !out_pinned)
+		CH = 1ull << 19; // bound by the host-side staging copies: few large ones (4.0 vs 4.6 ms)
 	if (c->chunk_log2 > 0)
 		CH = 1ull << c->chunk_log2;
 	CH = std::min<uint64_t>(std::min<uint64_t>(CH, 1ull << 19), n);
@@ -407,14 +449,56 @@ int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t 
 	}
 	enum { IN = 0, KERN = 1, OUT = 2 };
 	cudaStream_t s_in = c->pipe_stream[IN], s_k = c->pipe_stream[KERN], s_out = c->pipe_stream[OUT];
-	auto drain = [&](uint64_t k) -> cudaError_t { // chunk k's D2H is done: hand the records over
-		const int b = (int)(k % PIPE);
-		cudaError_t e = cudaEventSynchronize(c->ev_pipe[b][OUT]);
-		if (e == cudaSuccess) {
-			const uint64_t pf = start[k], pc = start[k + 1] - pf;
-			par_memcpy(static_cast<char *>(hits_out) + pf * hit_b, c->hits_pin[b].p, pc * hit_b);
+	// Pageable caller memory (a std::vector, as in the reference API) is staged through the pinned
+	// ring by two helper threads, so that copying rays in, enqueueing, and copying records out
+	// overlap: `producer` fills rays_pin[b] as soon as the H2D that last used it has left,
+	// `consumer` empties hits_pin[b] as soon as its D2H has arrived.
+	Progress pg;
+	std::thread producer, consumer;
+	struct Joiner { // every exit path: tell the helpers to leave, then wait for them
+		Progress &pg;
+		std::thread &a, &b;
+		~Joiner() {
+			pg.post([&] { pg.stop = true; });
+			if (a.joinable())
+				a.join();
+			if (b.joinable())
+				b.join();
 		}
-		return e;
+	} joiner{pg, producer, consumer};
+	if (!in_pinned)
+		producer = std::thread([&] {
+			cudaSetDevice(c->device);
+			for (uint64_t k = 0; k < n_chunks; ++k) {
+				const int b = (int)(k % PIPE);
+				if (k >= (uint64_t)PIPE) { // the H2D of chunk k-PIPE must have left the buffer
+					if (!pg.wait([&] { return pg.issued > k - PIPE; }))
+						return;
+					const cudaError_t e = cudaEventSynchronize(c->ev_pipe[b][IN]);
+					if (e != cudaSuccess)
+						return pg.fail(e);
+				}
+				par_memcpy(c->rays_pin[b].p, rays6 + start[k] * 6, (start[k + 1] - start[k]) * ray_b);
+				pg.post([&] { pg.produced = k + 1; });
+			}
+		});
+	if (!out_pinned)
+		consumer = std::thread([&] {
+			cudaSetDevice(c->device);
+			for (uint64_t k = 0; k < n_chunks; ++k) {
+				const int b = (int)(k % PIPE);
+				if (!pg.wait([&] { return pg.issued > k; }))
+					return;
+				const cudaError_t e = cudaEventSynchronize(c->ev_pipe[b][OUT]);
+				if (e != cudaSuccess)
+					return pg.fail(e);
+				par_memcpy(static_cast<char *>(hits_out) + start[k] * hit_b, c->hits_pin[b].p,
+				           (start[k + 1] - start[k]) * hit_b);
+				pg.post([&] { pg.consumed = k + 1; });
+			}
+		});
+	auto helper_failed = [&]() -> int {
+		return fail(c, PRT_E_CUDA, "nearest_hits: staging thread", pg.err);
 	};
 	// Three stages on three streams over a ring of PIPE buffer sets: the H2D engine, the SMs and
 	// the D2H engine each run back to back; a stage waits only for the event that frees what it
@@ -423,7 +507,6 @@ int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t 
 	PRT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
 	for (int k = 0; k < 3; ++k)
 		PRT_CUDA(c, cudaStreamWaitEvent(c->pipe_stream[k], c->ev0, 0));
-	uint64_t drained = 0; // pageable results: chunks [0, drained) are in the caller's array
 	// PRT_B200_PIPE_TRACE=1: device timeline of every stage of every chunk, printed to stderr
 	std::vector<cudaEvent_t> tl;
 	std::vector<double> host_us;
@@ -442,9 +525,8 @@ int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t 
 		// ---- H2D
 		const void *src = rays6 + first * 6;
 		if (!in_pinned) {
-			if (k >= (uint64_t)PIPE) // staging buffer b: its previous H2D must have left
-				PRT_CUDA(c, cudaEventSynchronize(c->ev_pipe[b][IN]));
-			par_memcpy(c->rays_pin[b].p, src, cnt * ray_b);
+			if (!pg.wait([&] { return pg.produced > k; }))
+				return helper_failed();
 			src = c->rays_pin[b].p;
 		}
 		if (k >= (uint64_t)PIPE) // device rays b: the kernel of chunk k-PIPE must have left
@@ -472,9 +554,9 @@ int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t 
 		mark(s_k);
 		PRT_CUDA(c, cudaEventRecord(c->ev_pipe[b][KERN], s_k));
 		// ---- D2H
-		if (!out_pinned && k >= (uint64_t)PIPE) { // staging buffer b still holds chunk k-PIPE
-			for (; drained <= k - PIPE; ++drained)
-				PRT_CUDA(c, drain(drained));
+		if (!out_pinned && k >= (uint64_t)PIPE) { // staging buffer b may still hold chunk k-PIPE
+			if (!pg.wait([&] { return pg.consumed > k - PIPE; }))
+				return helper_failed();
 		}
 		PRT_CUDA(c, cudaStreamWaitEvent(s_out, c->ev_pipe[b][KERN], 0));
 		void *dst = out_pinned ? static_cast<void *>(static_cast<char *>(hits_out) + first * hit_b)
@@ -483,20 +565,13 @@ int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t 
 		PRT_CUDA(c, cudaMemcpyAsync(dst, c->hits_dev[b].p, cnt * hit_b, cudaMemcpyDeviceToHost, s_out));
 		mark(s_out);
 		PRT_CUDA(c, cudaEventRecord(c->ev_pipe[b][OUT], s_out));
-		// pageable results: copy out whatever has already arrived, without waiting for it
-		if (!out_pinned)
-			while (drained < k) {
-				if (cudaEventQuery(c->ev_pipe[drained % PIPE][OUT]) != cudaSuccess) {
-					cudaGetLastError(); // "not ready" is not an error
-					break;
-				}
-				PRT_CUDA(c, drain(drained));
-				++drained;
-			}
+		pg.post([&] { pg.issued = k + 1; });
 	}
-	if (!out_pinned)
-		for (; drained < n_chunks; ++drained)
-			PRT_CUDA(c, drain(drained));
+	if (consumer.joinable()) { // it leaves after the last chunk has reached the caller's array
+		consumer.join();
+		if (pg.err != cudaSuccess)
+			return helper_failed();
+	}
 	// the last D2H depends on everything before it: join it into the context stream and time the
 	// whole call on the device
 	PRT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_pipe[(n_chunks - 1) % PIPE][OUT], 0));
