@@ -500,6 +500,31 @@ def main():
                     ts.append(ms)
             per_mask["_".join(combo)] = n_rays / (np.mean(ts) * 1e-3) / 1e6
 
+    # ---- opt-in watertight mode beside the default (reference arithmetic): its throughput and how
+    # many rays of this batch it answers differently
+    watertight = None
+    if world == 1 and mask & 2:
+        backend.trace_dev(d_rays.data_ptr(), n_rays, mask, **outs)
+        t_def = t.clone()
+        backend.set_triangle_test(1)
+        backend.set_tris_dev(d_tris.data_ptr(), n_tris)
+        ts = []
+        for k in range(7):
+            l2_flush()
+            ms = backend.trace_dev(d_rays.data_ptr(), n_rays, mask, **outs)
+            if k >= 2:
+                ts.append(ms)
+        hit_def, hit_wt = torch.isfinite(t_def), torch.isfinite(t)
+        both = hit_def & hit_wt
+        rel = ((t[both] - t_def[both]).abs() / t_def[both].abs().clamp_min(1e-30))
+        watertight = {"value": n_rays / (np.mean(ts) * 1e-3) / 1e6, "unit": "Mrays/s",
+                      "valid_differs": int((hit_def != hit_wt).sum().item()),
+                      "t_differs": int((t[both] != t_def[both]).sum().item()),
+                      "t_maxrel": float(rel.max().item()) if rel.numel() else 0.0,
+                      "note": "PRT_B200_WATERTIGHT=1 (Woop et al. 2013) vs the default on the same rays"}
+        backend.set_triangle_test(0)
+        backend.set_tris_dev(d_tris.data_ptr(), n_tris)
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -523,7 +548,7 @@ def main():
                             % len(numa_cpus) if numa_cpus else "no NUMA binding")},
         "build_mtris_s": build["mtris_s"], "build": build,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": cpu, "watertight": watertight,
         "wall_s_timed_region": wall, "device": backend.device_name(),
     }
     if per_mask:

@@ -127,6 +127,17 @@ int prt_b200_trace_dev_aos(prt_b200 *ctx, const float *d_rays6, uint64_t n_rays,
 /* Traversal knobs; opts == NULL restores the defaults. */
 int prt_b200_set_trace_opts(prt_b200 *ctx, const prt_trace_opts *opts);
 
+/* Triangle test: 0 (default) = the reference's Moeller-Trumbore arithmetic replayed operation for
+ * operation (core.hpp:27-65) -- results identical to the reference CPU backend; 1 = opt-in
+ * WATERTIGHT test (Woop, Benthin, Wald 2013): rays through an edge or vertex shared by two
+ * triangles can no longer slip between them, at the price of results that differ from the
+ * reference on exactly those grazing rays and by rounding of t, u, v.  Same result domain as the
+ * reference otherwise (signed t, minimum wins, no tmax).  Env PRT_B200_WATERTIGHT; takes effect at
+ * the next set_tris (the triangle records then keep the original vertices).
+ * prt_b200_triangle_test returns the mode the current scene was built for. */
+int prt_b200_set_triangle_test(prt_b200 *ctx, int mode);
+int prt_b200_triangle_test(const prt_b200 *ctx);
+
 /* Ray reordering in front of the traversal (results keep the caller's ray order): 0 = never,
  * 1 = always, 2 = automatic (default; env PRT_B200_SORT_RAYS): batches of >= 65 536 rays are
  * sorted by a 24-bit origin/direction key unless most neighbouring rays already share their key.

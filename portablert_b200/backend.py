@@ -159,6 +159,18 @@ class CUDABackend(Backend):
         self._need()
         self._check(lib().prt_b200_set_ray_sorting(self._h, int(mode)))
 
+    def set_triangle_test(self, mode: int):
+        """0 (default): the reference's Moeller-Trumbore arithmetic (core.hpp:27-65), results identical
+        to the reference; 1: opt-in watertight test (Woop et al. 2013).  Applies from the next
+        set_tris."""
+        self._need()
+        self._check(lib().prt_b200_set_triangle_test(self._h, int(mode)))
+
+    @property
+    def triangle_test(self) -> int:
+        self._need()
+        return int(lib().prt_b200_triangle_test(self._h))
+
     def set_wide_nodes(self, mode: int):
         """0 never, 1 always, 2 only for reordered (incoherent) batches; applies from the next set_tris."""
         self._need()

@@ -141,6 +141,8 @@ int prt_b200_create(prt_b200 **out, int device) {
 	c->sm_count = prop.multiProcessorCount;
 	if (const char *e = std::getenv("PRT_B200_FAST_BOXES"))
 		c->fast_boxes = std::atoi(e) != 0;
+	if (const char *e = std::getenv("PRT_B200_WATERTIGHT"))
+		c->watertight = std::atoi(e) != 0;
 	if (const char *e = std::getenv("PRT_B200_WIDE"))
 		c->wide_mode = std::max(0, std::min(2, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_SORT_RAYS"))
@@ -214,6 +216,14 @@ int prt_b200_set_wide_nodes(prt_b200 *c, int mode) {
 	c->wide_mode = mode;
 	return PRT_OK;
 }
+
+int prt_b200_set_triangle_test(prt_b200 *c, int mode) {
+	if (!c || mode < 0 || mode > 1)
+		return fail(c, PRT_E_ARG, "set_triangle_test: mode must be 0 or 1");
+	c->watertight = mode;
+	return PRT_OK;
+}
+int prt_b200_triangle_test(const prt_b200 *c) { return c && c->recs_vertex_form ? 1 : 0; }
 
 int prt_b200_set_ray_sorting(prt_b200 *c, int mode) {
 	if (!c || mode < 0 || mode > 2)

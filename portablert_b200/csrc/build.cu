@@ -252,7 +252,7 @@ __device__ __forceinline__ void merge_neighbours(bool &alive, int &l, int &r, in
 __global__ void __launch_bounds__(256)
     k_hierarchy(const float *__restrict__ tris9, const uint32_t *__restrict__ sorted_idx,
                 const uint64_t *__restrict__ keys, int n, TriRec *__restrict__ recs, Node *nodes,
-                int *bound, RootInfo *root_info) {
+                int *bound, RootInfo *root_info, bool vertex_form) {
 	__shared__ int s_cnt[8];
 	__shared__ int s_l[32], s_r[32], s_ref[32];
 	__shared__ float s_box[6][32];
@@ -270,10 +270,14 @@ __global__ void __launch_bounds__(256)
 			t[k] = __ldg(src + k);
 		b = tri_box(t);
 		float4 *rec = reinterpret_cast<float4 *>(recs + j);
-		// edges exactly as core.hpp:33-35 computes them
 		rec[0] = make_float4(t[0], t[1], t[2], __uint_as_float(prim));
-		rec[1] = make_float4(fsub(t[3], t[0]), fsub(t[4], t[1]), fsub(t[5], t[2]), b.lo[0]);
-		rec[2] = make_float4(fsub(t[6], t[0]), fsub(t[7], t[1]), fsub(t[8], t[2]), b.lo[1]);
+		if (vertex_form) { // watertight mode: the original vertices, shared ones bit-identical
+			rec[1] = make_float4(t[3], t[4], t[5], b.lo[0]);
+			rec[2] = make_float4(t[6], t[7], t[8], b.lo[1]);
+		} else { // edges exactly as core.hpp:33-35 computes them
+			rec[1] = make_float4(fsub(t[3], t[0]), fsub(t[4], t[1]), fsub(t[5], t[2]), b.lo[0]);
+			rec[2] = make_float4(fsub(t[6], t[0]), fsub(t[7], t[1]), fsub(t[8], t[2]), b.lo[1]);
+		}
 		rec[3] = make_float4(b.lo[2], b.hi[0], b.hi[1], b.hi[2]);
 	} else {
 #pragma unroll
@@ -378,7 +382,7 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     k_leaves(const float *__restrict__ tris9, const uint32_t *__restrict__ sorted_idx, uint64_t n,
-             TriRec *__restrict__ recs, float4 *__restrict__ leaf_box) {
+             TriRec *__restrict__ recs, float4 *__restrict__ leaf_box, bool vertex_form) {
 	const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= n)
 		return;
@@ -390,10 +394,14 @@ __global__ void __launch_bounds__(256)
 		t[k] = __ldg(src + k);
 	const Box b = tri_box(t);
 	float4 *rec = reinterpret_cast<float4 *>(recs + j);
-	// edges exactly as core.hpp:33-35 computes them
 	rec[0] = make_float4(t[0], t[1], t[2], __uint_as_float(prim));
-	rec[1] = make_float4(fsub(t[3], t[0]), fsub(t[4], t[1]), fsub(t[5], t[2]), b.lo[0]);
-	rec[2] = make_float4(fsub(t[6], t[0]), fsub(t[7], t[1]), fsub(t[8], t[2]), b.lo[1]);
+	if (vertex_form) {
+		rec[1] = make_float4(t[3], t[4], t[5], b.lo[0]);
+		rec[2] = make_float4(t[6], t[7], t[8], b.lo[1]);
+	} else { // edges exactly as core.hpp:33-35 computes them
+		rec[1] = make_float4(fsub(t[3], t[0]), fsub(t[4], t[1]), fsub(t[5], t[2]), b.lo[0]);
+		rec[2] = make_float4(fsub(t[6], t[0]), fsub(t[7], t[1]), fsub(t[8], t[2]), b.lo[1]);
+	}
 	rec[3] = make_float4(b.lo[2], b.hi[0], b.hi[1], b.hi[2]);
 	leaf_box[2 * j] = make_float4(b.lo[0], b.lo[1], b.lo[2], 0.0f);
 	leaf_box[2 * j + 1] = make_float4(b.hi[0], b.hi[1], b.hi[2], 0.0f);
@@ -510,6 +518,8 @@ int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 	c->n_tris = n;
 	c->n_nodes = n == 0 ? 0 : (n == 1 ? 1 : n - 1);
 	c->wide_built = false;
+	c->recs_vertex_form = c->watertight != 0;
+	const bool vf = c->recs_vertex_form;
 	if (n == 0)
 		return PRT_OK;
 	if (n > 0x7ffffffeull)
@@ -546,7 +556,7 @@ int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 	const int g = (int)((n + 255) / 256);
 	if (n == 1) {
 		k_leaves<<<1, 256, 0, s>>>(d_tris9, c->vals[cur].as<uint32_t>(), n, c->trirecs.as<TriRec>(),
-		                           c->leaf_box.as<float4>());
+		                           c->leaf_box.as<float4>(), vf);
 		k_single<<<1, 1, 0, s>>>(c->nodes.as<Node>(), c->trirecs.as<TriRec>(), c->leaf_box.as<float4>(),
 		                         c->root_info.as<RootInfo>());
 		c->launches += 2;
@@ -554,10 +564,10 @@ int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 		PRT_CUDA(c, cudaMemsetAsync(c->bound.p, 0xff, (n - 1) * 4, s));
 		k_hierarchy<<<g, 256, 0, s>>>(d_tris9, c->vals[cur].as<uint32_t>(), c->keys[cur].as<uint64_t>(),
 		                              (int)n, c->trirecs.as<TriRec>(), c->nodes.as<Node>(),
-		                              c->bound.as<int>(), c->root_info.as<RootInfo>());
+		                              c->bound.as<int>(), c->root_info.as<RootInfo>(), vf);
 		c->launches += 1;
 	}
-	c->wide_built = c->wide_mode == 1 || (c->wide_mode == 2 && n >= (1ull << 20));
+	c->wide_built = !vf && (c->wide_mode == 1 || (c->wide_mode == 2 && n >= (1ull << 20)));
 	if (c->wide_built) {
 		PRT_CUDA(c, c->nodes4.reserve(c->n_nodes * sizeof(Node4)));
 		k_wide<<<(int)((c->n_nodes + 255) / 256), 256, 0, s>>>(c->nodes.as<Node>(), (int)c->n_nodes,

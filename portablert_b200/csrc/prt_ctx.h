@@ -109,6 +109,8 @@ struct prt_b200 {
 	prt_trace_opts opts{1, 1e-4f, 64.0f};
 
 	float scene_absmax[3] = {0.f, 0.f, 0.f}; // largest |coordinate| per axis (fast box-test margin)
+	int watertight = 0;                      // env PRT_B200_WATERTIGHT / prt_b200_set_triangle_test: takes effect at set_tris
+	bool recs_vertex_form = false;           // the current triangle records hold v1, v2 (watertight) instead of the edges
 	int fast_boxes = 1;                      // env PRT_B200_FAST_BOXES=0 forces the exact test everywhere
 	int refill = 16;                         // env PRT_B200_REFILL: dynamic ray-fetch threshold (lanes)
 	int chunk_log2 = 0; // host entry point: rays per pipeline chunk (0 = automatic)

@@ -267,6 +267,100 @@ PRT_HD bool moller_trumbore_ref(const RayC &r, const float *v0, const float *e1,
 	return true;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Opt-in WATERTIGHT triangle test (Woop, Benthin, Wald: "Watertight Ray/Triangle Intersection",
+// JCGT 2013).  Not the reference's arithmetic: intersect_tri (core.hpp:27-65) can miss rays that
+// pass exactly through an edge or vertex shared by two triangles, because each triangle rounds
+// its own u, v differently.  Here the three edge functions are evaluated in a ray-aligned sheared
+// space from the ORIGINAL vertices with un-fused multiplies and subtracts, so the edge function
+// of a shared edge is the same number (negated) in both triangles and one of them always
+// accepts the ray; an exactly-zero edge function is re-evaluated in binary64, where the products
+// of binary32 values are exact and the sign is therefore the true one.  The mode keeps the
+// reference's result domain (signed t, minimum wins, no tmax, no back-face culling) and its
+// (u, v) = weights of v1, v2, so it differs from the default only on edge/vertex grazing rays and
+// by rounding of t, u, v; tests/ and bench.py count those differences against the oracle.
+struct WoopRay {
+	int kx, ky, kz;
+	float Sx, Sy, Sz;
+};
+
+PRT_HD float pick3(const float *a, int k) { return k == 0 ? a[0] : (k == 1 ? a[1] : a[2]); }
+
+PRT_HD WoopRay make_woop_ray(const RayC &r) {
+	WoopRay w;
+	const float ax = fabsf(r.d[0]), ay = fabsf(r.d[1]), az = fabsf(r.d[2]);
+	w.kz = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
+	w.kx = w.kz == 2 ? 0 : w.kz + 1;
+	w.ky = w.kx == 2 ? 0 : w.kx + 1;
+	const float dz = pick3(r.d, w.kz);
+	if (dz < 0.0f) { // keep the winding
+		const int tmp = w.kx;
+		w.kx = w.ky;
+		w.ky = tmp;
+	}
+	w.Sx = fdiv(pick3(r.d, w.kx), dz);
+	w.Sy = fdiv(pick3(r.d, w.ky), dz);
+	w.Sz = fdiv(1.0f, dz);
+	return w;
+}
+
+// a, b, c: the triangle's vertices as given (core.hpp:24); u, v: weights of b and c like core.hpp
+PRT_HD bool woop_watertight(const RayC &r, const WoopRay &w, const float *a, const float *b,
+                            const float *c, float &t, float &u, float &v) {
+	const float A[3] = {fsub(a[0], r.o[0]), fsub(a[1], r.o[1]), fsub(a[2], r.o[2])};
+	const float B[3] = {fsub(b[0], r.o[0]), fsub(b[1], r.o[1]), fsub(b[2], r.o[2])};
+	const float C[3] = {fsub(c[0], r.o[0]), fsub(c[1], r.o[1]), fsub(c[2], r.o[2])};
+	const float Akz = pick3(A, w.kz), Bkz = pick3(B, w.kz), Ckz = pick3(C, w.kz);
+	const float Ax = fsub(pick3(A, w.kx), fmul(w.Sx, Akz)), Ay = fsub(pick3(A, w.ky), fmul(w.Sy, Akz));
+	const float Bx = fsub(pick3(B, w.kx), fmul(w.Sx, Bkz)), By = fsub(pick3(B, w.ky), fmul(w.Sy, Bkz));
+	const float Cx = fsub(pick3(C, w.kx), fmul(w.Sx, Ckz)), Cy = fsub(pick3(C, w.ky), fmul(w.Sy, Ckz));
+	float U = fsub(fmul(Cx, By), fmul(Cy, Bx));
+	float V = fsub(fmul(Ax, Cy), fmul(Ay, Cx));
+	float W = fsub(fmul(Bx, Ay), fmul(By, Ax));
+	if (U == 0.0f || V == 0.0f || W == 0.0f) {
+		// products of two binary32 values are exact in binary64: the sign of the difference is exact
+		U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
+		V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+		W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+	}
+	if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f))
+		return false;
+	const float det = fadd(fadd(U, V), W);
+	if (det == 0.0f)
+		return false;
+	const float Az = fmul(w.Sz, Akz), Bz = fmul(w.Sz, Bkz), Cz = fmul(w.Sz, Ckz);
+	const float T = fadd(fadd(fmul(U, Az), fmul(V, Bz)), fmul(W, Cz));
+	const float inv = fdiv(1.0f, det);
+	t = fmul(T, inv);
+	u = fmul(V, inv);
+	v = fmul(W, inv);
+	return true;
+}
+
+// Box test of the watertight mode where the fast test does not apply: the reference's slab formula
+// made conservative with respect to the exact line.  (a) A NaN plane parameter -- 0 * inf: the ray
+// runs parallel to an axis and lies exactly in a face plane of the box -- makes that axis
+// unbounded instead of poisoning or, with NaN-dropping min/max, wrongly closing the interval.
+// (b) The interval is widened by 2^-21 relative: each bound carries at most three roundings of
+// 2^-24.  Keeps the reference's domain rule "tmax >= 0" (bvh.hpp:215).
+PRT_HD bool slab_cons(const RayC &r, const float *lo, const float *hi, float &tmin_out) {
+	float tmin = -INFINITY, tmax = INFINITY;
+#pragma unroll
+	for (int a = 0; a < 3; ++a) {
+		const float tl = fmul(fsub(lo[a], r.o[a]), r.idir[a]);
+		const float th = fmul(fsub(hi[a], r.o[a]), r.idir[a]);
+		const bool nan = !(tl == tl) || !(th == th);
+		tmin = fmaxf(tmin, nan ? -INFINITY : fminf(tl, th));
+		tmax = fminf(tmax, nan ? INFINITY : fmaxf(tl, th));
+	}
+	const float eps = 4.76837158e-7f; // 2^-21
+	// (the widening term is kept finite so that an infinite bound stays infinite, not NaN)
+	tmin = fsub(tmin, fmul(fminf(fabsf(tmin), 3.0e38f), eps));
+	tmax = fadd(tmax, fmul(fminf(fabsf(tmax), 3.0e38f), eps));
+	tmin_out = tmin;
+	return !(tmax < 0.0f) && !(tmin > tmax);
+}
+
 // Best-hit update.  The reference keeps the first-visited triangle among equal t (strict <,
 // bvh.hpp:247); its visit order is an artefact of its own SAH tree, so this backend defines a
 // deterministic, traversal-order-independent rule instead: lowest primitive_id among equal t.

@@ -244,10 +244,15 @@ PRT_HD bool wide_node_step(TravState &s, StackEntry *stack, const Node4 *nodes4,
 	return false;
 }
 
-template <bool ANYHIT, bool WANT_UV, bool TRACK_PRIM, bool COUNT, bool FAST, bool WIDE = false>
+// WT = opt-in watertight mode (prt_math.cuh: woop_watertight): triangle records carry the original
+// vertices (v1, v2 in place of the edges), every box test is conservative with respect to the exact
+// line (fast test with its margin, or slab_cons), and the triangle's own box keeps only the
+// reference's domain rule.
+template <bool ANYHIT, bool WANT_UV, bool TRACK_PRIM, bool COUNT, bool FAST, bool WIDE = false,
+          bool WT = false>
 PRT_HD void trav_step(TravState &s, StackEntry *stack, const Node *nodes, const TriRec *tris,
                       const RayC &r, const FastRay &fr, const TraverseOpts &opt,
-                      const Node4 *nodes4 = nullptr) {
+                      const Node4 *nodes4 = nullptr, const WoopRay *wr = nullptr) {
 	bool pop = true;
 	if (WIDE && s.cur >= 0) {
 		if (COUNT)
@@ -266,6 +271,9 @@ PRT_HD void trav_step(TravState &s, StackEntry *stack, const Node *nodes, const 
 		if (FAST) {
 			h0 = slab_fast(fr, lo0, hi0, tm0) && !(tm0 > s.limitM);
 			h1 = slab_fast(fr, lo1, hi1, tm1) && !(tm1 > s.limitM);
+		} else if (WT) {
+			h0 = slab_cons(r, lo0, hi0, tm0) && !(tm0 > s.limit);
+			h1 = slab_cons(r, lo1, hi1, tm1) && !(tm1 > s.limit);
 		} else {
 			h0 = slab_ref(r, lo0, hi0, tm0) && !(tm0 > s.limit);
 			h1 = slab_ref(r, lo1, hi1, tm1) && !(tm1 > s.limit);
@@ -295,7 +303,9 @@ PRT_HD void trav_step(TravState &s, StackEntry *stack, const Node *nodes, const 
 		const float e2[3] = {q2.x, q2.y, q2.z};
 		const uint32_t prim = f2u(q0.w);
 		float t, u, v;
-		if (moller_trumbore_ref(r, v0, e1, e2, t, u, v)) {
+		// (watertight records: e1, e2 hold the vertices v1, v2)
+		if (WT ? woop_watertight(r, *wr, v0, e1, e2, t, u, v)
+		       : moller_trumbore_ref(r, v0, e1, e2, t, u, v)) {
 			const bool better = ANYHIT ? (t < s.t_best)
 			                           : (TRACK_PRIM ? closer(t, prim, s.t_best, s.prim_best)
 			                                         : (t < s.t_best));
@@ -303,7 +313,7 @@ PRT_HD void trav_step(TravState &s, StackEntry *stack, const Node *nodes, const 
 			if (FAST && better) {
 				const float lo[3] = {q1.w, q2.w, q3.x}, hi[3] = {q3.y, q3.z, q3.w};
 				float tm;
-				box_ok = slab_ref(r, lo, hi, tm);
+				box_ok = WT ? slab_cons(r, lo, hi, tm) : slab_ref(r, lo, hi, tm);
 			}
 			if (better && box_ok) {
 				if (ANYHIT) {
@@ -341,16 +351,20 @@ PRT_HD void trav_step(TravState &s, StackEntry *stack, const Node *nodes, const 
 }
 
 // Scalar driver (instrumented kernel and the host-side emulator): one ray start to finish.
-template <bool ANYHIT, bool WANT_UV, bool TRACK_PRIM, bool COUNT, bool FAST, bool WIDE = false>
+template <bool ANYHIT, bool WANT_UV, bool TRACK_PRIM, bool COUNT, bool FAST, bool WIDE = false,
+          bool WT = false>
 PRT_HD void traverse(const Node *nodes, const TriRec *tris, uint64_t n_tris_scene, int32_t root,
                      const RayC &r, const FastRay &fr, const TraverseOpts &opt, Hit &out,
                      const Node4 *nodes4 = nullptr) {
 	TravState s;
 	StackEntry stack[STACK_DEPTH];
 	trav_init(s, r, opt, n_tris_scene, root);
+	WoopRay wr{};
+	if (WT)
+		wr = make_woop_ray(r);
 	while (s.cur != PRT_DONE)
-		trav_step<ANYHIT, WANT_UV, TRACK_PRIM, COUNT, FAST, WIDE>(s, stack, nodes, tris, r, fr, opt,
-		                                                          nodes4);
+		trav_step<ANYHIT, WANT_UV, TRACK_PRIM, COUNT, FAST, WIDE, WT>(s, stack, nodes, tris, r, fr,
+		                                                              opt, nodes4, &wr);
 	out.t = s.t_best;
 	out.u = s.u_best;
 	out.v = s.v_best;

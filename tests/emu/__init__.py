@@ -24,7 +24,7 @@ class Emu:
         build()
         L = C.CDLL(LIB)
         L.emu_build.restype = C.c_void_p
-        L.emu_build.argtypes = [C.c_void_p, C.c_uint64, C.c_int]
+        L.emu_build.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int]
         L.emu_load.restype = C.c_void_p
         L.emu_load.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int32]
         L.emu_free.argtypes = [C.c_void_p]
@@ -33,15 +33,15 @@ class Emu:
         L.emu_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_download_wide.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_float, C.c_float,
-                                C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8
+                                C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8
         self.L = L
         self.h = None
 
-    def build(self, tris, bits=16):
+    def build(self, tris, bits=16, watertight=False):
         tris = np.ascontiguousarray(tris, np.float32).reshape(-1, 9)
         self.free()
         self.n = len(tris)
-        self.h = self.L.emu_build(tris.ctypes.data, len(tris), bits)
+        self.h = self.L.emu_build(tris.ctypes.data, len(tris), bits, int(watertight))
         return self
 
     def load(self, nodes, tris, root=0):
@@ -70,7 +70,8 @@ class Emu:
         self.L.emu_download_wide(self.h, out.ctypes.data)
         return out
 
-    def trace(self, rays, prune=1, slack_rel=1e-4, slack_ulps=64.0, anyhit=False, fast=True, wide=False):
+    def trace(self, rays, prune=1, slack_rel=1e-4, slack_ulps=64.0, anyhit=False, fast=True, wide=False,
+              watertight=False):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
         n = len(rays)
         o = {k: np.empty(n, np.float32) for k in ("t", "u", "v")}
@@ -80,7 +81,7 @@ class Emu:
         cnt = np.zeros((n, 2), np.uint32)
         ff = np.zeros(n, np.uint8)
         self.L.emu_trace(self.h, rays.ctypes.data, n, int(prune), slack_rel, slack_ulps,
-                         int(anyhit), int(fast), int(wide), o["t"].ctypes.data, o["u"].ctypes.data, o["v"].ctypes.data,
+                         int(anyhit), int(fast), int(wide), int(watertight), o["t"].ctypes.data, o["u"].ctypes.data, o["v"].ctypes.data,
                          o["pid"].ctypes.data, o["valid"].ctypes.data, p.ctypes.data,
                          cnt.ctypes.data, ff.ctypes.data)
         o["fast"] = ff.astype(bool)

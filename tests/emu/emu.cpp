@@ -89,7 +89,7 @@ Box refit(Emu &e, const std::vector<Box> &leaf, int32_t ref) {
 
 extern "C" {
 
-void *emu_build(const float *tris9, uint64_t n, int bits) {
+void *emu_build(const float *tris9, uint64_t n, int bits, int vertex_form) {
 	Emu *e = new Emu();
 	e->n = n;
 	if (n == 0)
@@ -132,8 +132,8 @@ void *emu_build(const float *tris9, uint64_t n, int bits) {
 		std::memset(&r, 0, sizeof r);
 		for (int a = 0; a < 3; ++a) {
 			r.v0[a] = t[a];
-			r.e1[a] = t[3 + a] - t[a];
-			r.e2[a] = t[6 + a] - t[a];
+			r.e1[a] = vertex_form ? t[3 + a] : t[3 + a] - t[a];
+			r.e2[a] = vertex_form ? t[6 + a] : t[6 + a] - t[a];
 		}
 		r.prim = idx[j];
 		r.lox = leaf[j].lo[0];
@@ -154,8 +154,8 @@ void *emu_build(const float *tris9, uint64_t n, int bits) {
 		nd.child0 = ~0;
 		nd.child1 = ~1;
 		TriRec dummy = e->tris[0]; // zero-area: det == 0, never hit
-		for (int a = 0; a < 3; ++a)
-			dummy.e1[a] = dummy.e2[a] = 0.0f;
+		for (int a = 0; a < 3; ++a) // (vertex form: all three vertices coincide)
+			dummy.e1[a] = dummy.e2[a] = vertex_form ? dummy.v0[a] : 0.0f;
 		dummy.prim = 0xffffffffu;
 		e->tris.push_back(dummy);
 		e->bounds();
@@ -207,7 +207,7 @@ void *emu_load(const void *nodes, uint64_t n_nodes, const void *tris, uint64_t n
 // SoA outputs like the device entry point; counts (2 per ray) may be NULL.  anyhit=1 emulates the
 // `valid`-only specialisation.
 void emu_trace(void *h, const float *rays6, uint64_t n, int prune, float slack_rel, float slack_ulps,
-               int anyhit, int fast, int wide, float *t, float *u, float *v, uint32_t *pid, uint8_t *valid, float *p,
+               int anyhit, int fast, int wide, int wt, float *t, float *u, float *v, uint32_t *pid, uint8_t *valid, float *p,
                uint32_t *counts, uint8_t *fastflag) {
 	Emu *e = static_cast<Emu *>(h);
 	TraverseOpts o{prune, slack_rel, slack_ulps};
@@ -217,7 +217,15 @@ void emu_trace(void *h, const float *rays6, uint64_t n, int prune, float slack_r
 		const FastRay fr = make_fast_ray(r, e->absmax);
 		const bool f = fast && fr.ok; // per ray here; the kernel votes per warp
 		const Node4 *n4 = e->nodes4.data();
-		if (wide && f && anyhit)
+		if (wt && anyhit && f)
+			traverse<true, false, false, false, true, false, true>(e->nodes.data(), e->tris.data(), e->n, e->root, r, fr, o, hit);
+		else if (wt && anyhit)
+			traverse<true, false, false, false, false, false, true>(e->nodes.data(), e->tris.data(), e->n, e->root, r, fr, o, hit);
+		else if (wt && f)
+			traverse<false, true, true, true, true, false, true>(e->nodes.data(), e->tris.data(), e->n, e->root, r, fr, o, hit);
+		else if (wt)
+			traverse<false, true, true, true, false, false, true>(e->nodes.data(), e->tris.data(), e->n, e->root, r, fr, o, hit);
+		else if (wide && f && anyhit)
 			traverse<true, false, false, false, true, true>(e->nodes.data(), e->tris.data(), e->n, e->root, r, fr, o, hit, n4);
 		else if (wide && f)
 			traverse<false, true, true, true, true, true>(e->nodes.data(), e->tris.data(), e->n, e->root, r, fr, o, hit, n4);
