@@ -521,6 +521,7 @@ def main():
                       "valid_differs": int((hit_def != hit_wt).sum().item()),
                       "t_differs": int((t[both] != t_def[both]).sum().item()),
                       "t_maxrel": float(rel.max().item()) if rel.numel() else 0.0,
+                      "t_rel_gt_1e-5": int((rel > 1e-5).sum().item()),
                       "note": "PRT_B200_WATERTIGHT=1 (Woop et al. 2013) vs the default on the same rays"}
         backend.set_triangle_test(0)
         backend.set_tris_dev(d_tris.data_ptr(), n_tris)

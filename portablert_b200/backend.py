@@ -159,6 +159,17 @@ class CUDABackend(Backend):
         self._need()
         self._check(lib().prt_b200_set_ray_sorting(self._h, int(mode)))
 
+    def set_treelet_passes(self, passes: int):
+        """Opt-in SAH optimisation of the tree inside set_tris (treelet restructuring, Karras & Aila
+        2013); 0 = off (default).  Applies from the next set_tris."""
+        self._need()
+        self._check(lib().prt_b200_set_treelet_passes(self._h, int(passes)))
+
+    @property
+    def tree_depth(self) -> int:
+        self._need()
+        return int(lib().prt_b200_tree_depth(self._h))
+
     def set_triangle_test(self, mode: int):
         """0 (default): the reference's Moeller-Trumbore arithmetic (core.hpp:27-65), results identical
         to the reference; 1: opt-in watertight test (Woop et al. 2013).  Applies from the next

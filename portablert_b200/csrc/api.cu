@@ -141,6 +141,8 @@ int prt_b200_create(prt_b200 **out, int device) {
 	c->sm_count = prop.multiProcessorCount;
 	if (const char *e = std::getenv("PRT_B200_FAST_BOXES"))
 		c->fast_boxes = std::atoi(e) != 0;
+	if (const char *e = std::getenv("PRT_B200_TREELET"))
+		c->treelet_passes = std::max(0, std::min(8, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_WATERTIGHT"))
 		c->watertight = std::atoi(e) != 0;
 	if (const char *e = std::getenv("PRT_B200_WIDE"))
@@ -217,6 +219,14 @@ int prt_b200_set_wide_nodes(prt_b200 *c, int mode) {
 	return PRT_OK;
 }
 
+int prt_b200_set_treelet_passes(prt_b200 *c, int passes) {
+	if (!c || passes < 0 || passes > 8)
+		return fail(c, PRT_E_ARG, "set_treelet_passes: passes must be in 0..8");
+	c->treelet_passes = passes;
+	return PRT_OK;
+}
+int32_t prt_b200_tree_depth(const prt_b200 *c) { return c ? c->tree_depth : 0; }
+
 int prt_b200_set_triangle_test(prt_b200 *c, int mode) {
 	if (!c || mode < 0 || mode > 1)
 		return fail(c, PRT_E_ARG, "set_triangle_test: mode must be 0 or 1");
@@ -254,12 +264,21 @@ static int timed_build(prt_b200 *c, const float *d_tris9, uint64_t n, float *ms)
 	struct {
 		int32_t root;
 		float lo[3], hi[3];
-		int32_t pad;
+		int32_t depth;
 	} ri{};
 	if (c->n_nodes)
 		PRT_CUDA(c, cudaMemcpyAsync(&ri, c->root_info.p, sizeof ri, cudaMemcpyDeviceToHost, c->stream));
 	PRT_CUDA(c, cudaStreamSynchronize(c->stream));
 	PRT_CUDA(c, cudaEventElapsedTime(&c->last_build_ms, c->ev0, c->ev1));
+	// The traversal stack is sized for the radix tree's depth bound (prt_traverse.cuh); treelet
+	// restructuring has no such bound, so a tree that came out deeper is rebuilt without it.
+	c->tree_depth = c->n_nodes ? ri.depth : 0;
+	if (c->tree_depth > 96 && !c->treelet_suspended) {
+		c->treelet_suspended = true;
+		rc = timed_build(c, d_tris9, n, ms);
+		c->treelet_suspended = false;
+		return rc;
+	}
 	c->root = c->n_nodes ? ri.root : 0;
 	for (int a = 0; a < 3; ++a) {
 		c->scene_lo[a] = c->n_nodes ? ri.lo[a] : 0.f;

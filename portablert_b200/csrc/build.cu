@@ -17,6 +17,7 @@
 #include <cstdlib>
 
 #include "prt_ctx.h"
+#include "prt_treelet.cuh"
 
 namespace prt {
 
@@ -173,7 +174,7 @@ __device__ __forceinline__ bool delta_less(const uint64_t *__restrict__ keys, in
 struct RootInfo {
 	int32_t root;
 	float lo[3], hi[3];
-	int32_t pad;
+	int32_t depth; // height of the tree, written by the treelet pass (0 = not measured)
 };
 
 // Shuffle phase shared by the warp and block levels: the alive lanes of the calling warp carry
@@ -189,6 +190,7 @@ __device__ __forceinline__ void merge_neighbours(bool &alive, int &l, int &r, in
 		const unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
 		if (alive && l == 0 && r == n - 1) { // the root: publish its index and the scene box
 			root_info->root = ref;
+			root_info->depth = 0;
 #pragma unroll
 			for (int a = 0; a < 3; ++a) {
 				root_info->lo[a] = b.lo[a];
@@ -367,6 +369,7 @@ __global__ void __launch_bounds__(256)
 		ref = p;
 		if (l == 0 && r == n - 1) { // the root: publish its index and the scene box
 			root_info->root = p;
+			root_info->depth = 0;
 #pragma unroll
 			for (int a = 0; a < 3; ++a) {
 				root_info->lo[a] = b.lo[a];
@@ -423,6 +426,7 @@ __global__ void k_single(Node *nodes, TriRec *recs, const float4 *leaf_box, Root
 	nd.pad0 = nd.pad1 = 0;
 	nodes[0] = nd;
 	root_info->root = 0;
+	root_info->depth = 0;
 	root_info->lo[0] = lo.x;
 	root_info->lo[1] = lo.y;
 	root_info->lo[2] = lo.z;
@@ -434,6 +438,66 @@ __global__ void k_single(Node *nodes, TriRec *recs, const float4 *leaf_box, Root
 	rec[1] = make_float4(0.f, 0.f, 0.f, lo.x);
 	rec[2] = make_float4(0.f, 0.f, 0.f, lo.y);
 	rec[3] = make_float4(lo.z, hi.x, hi.y, hi.z);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 5b. opt-in SAH optimisation: bottom-up treelet restructuring (prt_treelet.cuh)
+// ------------------------------------------------------------------------------------------------
+// parent links of the current tree (the hierarchy kernel needs none); rebuilt before every pass
+__global__ void __launch_bounds__(256)
+    k_parents(const Node *__restrict__ nodes, int n_nodes, int32_t *__restrict__ parent,
+              int32_t *__restrict__ leaf_parent) {
+	const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+	if (i >= n_nodes)
+		return;
+	const int4 tail = __ldg(reinterpret_cast<const int4 *>(nodes + i) + 3);
+	const int32_t c0 = tail.x, c1 = tail.y;
+	if (c0 >= 0)
+		parent[c0] = i;
+	else
+		leaf_parent[~c0] = i;
+	if (c1 >= 0)
+		parent[c1] = i;
+	else
+		leaf_parent[~c1] = i;
+}
+
+// One thread per triangle climbs towards the root; at every internal node the first arrival
+// retires and the second one -- which therefore sees both finished subtrees -- optimises the
+// treelet rooted there (if at least TREELET_N triangles hang below) and carries on.  A treelet only
+// rewrites nodes inside the subtree of its root, which no other thread touches any more, and what
+// it writes depends only on that subtree: the result does not depend on arrival order.
+__global__ void __launch_bounds__(128)
+    k_treelet(Node *nodes, int n_tris, const int32_t *__restrict__ parent,
+              const int32_t *__restrict__ leaf_parent, unsigned *flag, int32_t *count, int32_t *depth,
+              RootInfo *root_info) {
+	const int j = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+	if (j >= n_tris)
+		return;
+	const int32_t root = root_info->root;
+	int32_t cur = leaf_parent[j];
+	for (;;) {
+		__threadfence(); // release what this thread wrote below `cur`
+		if (atomicAdd(flag + cur, 1u) == 0u)
+			return;
+		__threadfence(); // acquire the sibling subtree
+		const int4 tail = __ldcg(reinterpret_cast<const int4 *>(nodes + cur) + 3);
+		const int32_t c0 = tail.x, c1 = tail.y;
+		const int32_t n0 = c0 < 0 ? 1 : __ldcg(count + c0), n1 = c1 < 0 ? 1 : __ldcg(count + c1);
+		const int32_t total = n0 + n1;
+		if (total >= TREELET_N) {
+			treelet_optimise(nodes, cur, depth);
+		} else {
+			const int32_t d0 = c0 < 0 ? 0 : __ldcg(depth + c0), d1 = c1 < 0 ? 0 : __ldcg(depth + c1);
+			depth[cur] = 1 + max(d0, d1);
+		}
+		count[cur] = total;
+		if (cur == root) {
+			root_info->depth = depth[cur];
+			return;
+		}
+		cur = parent[cur];
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -566,6 +630,25 @@ int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 		                              (int)n, c->trirecs.as<TriRec>(), c->nodes.as<Node>(),
 		                              c->bound.as<int>(), c->root_info.as<RootInfo>(), vf);
 		c->launches += 1;
+	}
+	// opt-in SAH optimisation of the tree just built (env PRT_B200_TREELET = number of passes)
+	if (c->treelet_passes > 0 && !c->treelet_suspended && n >= (uint64_t)TREELET_N) {
+		PRT_CUDA(c, c->tl_parent.reserve((n - 1) * 4));
+		PRT_CUDA(c, c->tl_leaf_parent.reserve(n * 4));
+		PRT_CUDA(c, c->tl_flag.reserve((n - 1) * 4));
+		PRT_CUDA(c, c->tl_count.reserve((n - 1) * 4));
+		PRT_CUDA(c, c->tl_depth.reserve((n - 1) * 4));
+		for (int pass = 0; pass < c->treelet_passes; ++pass) {
+			PRT_CUDA(c, cudaMemsetAsync(c->tl_flag.p, 0, (n - 1) * 4, s));
+			k_parents<<<(int)((n - 1 + 255) / 256), 256, 0, s>>>(c->nodes.as<Node>(), (int)(n - 1),
+			                                                    c->tl_parent.as<int32_t>(),
+			                                                    c->tl_leaf_parent.as<int32_t>());
+			k_treelet<<<(int)((n + 127) / 128), 128, 0, s>>>(
+			    c->nodes.as<Node>(), (int)n, c->tl_parent.as<int32_t>(), c->tl_leaf_parent.as<int32_t>(),
+			    c->tl_flag.as<unsigned>(), c->tl_count.as<int32_t>(), c->tl_depth.as<int32_t>(),
+			    c->root_info.as<RootInfo>());
+			c->launches += 2;
+		}
 	}
 	c->wide_built = !vf && (c->wide_mode == 1 || (c->wide_mode == 2 && n >= (1ull << 20)));
 	if (c->wide_built) {

@@ -89,6 +89,11 @@ struct prt_b200 {
 
 	// build scratch
 	prt::DevBuf keys[2], vals[2], sort_scratch, bounds, leaf_box, bound, root_info;
+	// opt-in treelet SAH optimisation (build.cu 5b): parent links, arrival flags, leaf counts, heights
+	prt::DevBuf tl_parent, tl_leaf_parent, tl_flag, tl_count, tl_depth;
+	int treelet_passes = 0;         // env PRT_B200_TREELET / prt_b200_set_treelet_passes: 0 = off (default)
+	bool treelet_suspended = false; // the optimised tree got deeper than the traversal stack allows
+	int32_t tree_depth = 0;         // height of the optimised tree (0 = not measured)
 	int32_t root = 0; // index of the root node (the radix tree numbers nodes by split position)
 
 	// trace scratch

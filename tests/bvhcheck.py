@@ -64,3 +64,14 @@ def check_bvh(nodes, trirecs, tris, root=0):
                 hi[node] = np.maximum(hi[node], ehi)
     assert seen_leaf.all() and seen_node.all()
     return depth
+
+
+def sah_internal_area(nodes, root=0):
+    """sum of the internal nodes' half surface areas relative to the root's (the SAH cost of a tree
+    with one triangle per leaf, up to constants)"""
+    b = nodes[:, :12].astype(np.float64)
+    lo = np.minimum(b[:, 0:3], b[:, 6:9])
+    hi = np.maximum(b[:, 3:6], b[:, 9:12])
+    d = hi - lo
+    a = d[:, 0] * d[:, 1] + d[:, 1] * d[:, 2] + d[:, 2] * d[:, 0]
+    return float(a.sum() / a[root])

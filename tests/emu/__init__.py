@@ -12,7 +12,8 @@ CSRC = os.path.join(HERE, "..", "..", "portablert_b200", "csrc")
 
 
 def build():
-    deps = [SRC, os.path.join(CSRC, "prt_math.cuh"), os.path.join(CSRC, "prt_traverse.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, h) for h in ("prt_math.cuh", "prt_traverse.cuh",
+                                                      "prt_treelet.cuh")]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", LIB,
@@ -28,6 +29,8 @@ class Emu:
         L.emu_load.restype = C.c_void_p
         L.emu_load.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int32]
         L.emu_free.argtypes = [C.c_void_p]
+        L.emu_treelet.restype = C.c_int32
+        L.emu_treelet.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
         L.emu_num_nodes.restype = C.c_uint64
         L.emu_num_nodes.argtypes = [C.c_void_p]
         L.emu_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -51,6 +54,12 @@ class Emu:
         self.n = tris.nbytes // 64
         self.h = self.L.emu_load(nodes.ctypes.data, nodes.nbytes // 64, tris.ctypes.data, self.n, root)
         return self
+
+    def treelet(self, passes=1):
+        """opt-in SAH optimisation (prt_treelet.cuh) -> (tree height, treelets changed in last pass)"""
+        ch = C.c_uint64(0)
+        d = self.L.emu_treelet(self.h, int(passes), C.byref(ch))
+        return int(d), int(ch.value)
 
     def free(self):
         if self.h:

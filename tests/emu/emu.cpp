@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../portablert_b200/csrc/prt_traverse.cuh"
+#include "../../portablert_b200/csrc/prt_treelet.cuh"
 
 using namespace prt;
 
@@ -87,7 +88,40 @@ Box refit(Emu &e, const std::vector<Box> &leaf, int32_t ref) {
 }
 } // namespace
 
+// sequential stand-in for k_treelet (build.cu): children before parents, same per-node rule
+int32_t treelet_walk(Emu &e, int32_t x, std::vector<int32_t> &depth, int32_t &count, uint64_t &changed) {
+	const int32_t c0 = e.nodes[x].child0, c1 = e.nodes[x].child1;
+	int32_t n0 = 1, n1 = 1;
+	const int32_t d0 = c0 < 0 ? 0 : treelet_walk(e, c0, depth, n0, changed);
+	const int32_t d1 = c1 < 0 ? 0 : treelet_walk(e, c1, depth, n1, changed);
+	count = n0 + n1;
+	if (count >= TREELET_N)
+		changed += treelet_optimise(e.nodes.data(), x, depth.data()) ? 1 : 0;
+	else
+		depth[x] = 1 + std::max(d0, d1);
+	return depth[x];
+}
+
 extern "C" {
+
+// `passes` rounds of treelet restructuring; returns the height of the tree, *changed = treelets
+// whose topology was replaced in the last pass
+int32_t emu_treelet(void *h, int passes, uint64_t *changed) {
+	Emu *e = static_cast<Emu *>(h);
+	if (e->n < (uint64_t)TREELET_N)
+		return 0;
+	std::vector<int32_t> depth(e->nodes.size(), 0);
+	int32_t d = 0;
+	for (int p = 0; p < passes; ++p) {
+		int32_t cnt = 0;
+		uint64_t ch = 0;
+		d = treelet_walk(*e, e->root, depth, cnt, ch);
+		if (changed)
+			*changed = ch;
+	}
+	e->bounds();
+	return d;
+}
 
 void *emu_build(const float *tris9, uint64_t n, int bits, int vertex_form) {
 	Emu *e = new Emu();

@@ -274,3 +274,34 @@ def test_watertight_mode_closes_the_cracks_of_the_reference_test(oracle, emu):
     rep = parity.compare(ref, wt, tris, rays, None)
     assert rep["valid_mismatch"] <= 2 and rep["pid_mismatch"] <= 2, rep
     assert rep["t_maxrel"] <= parity.T_REL and rep["u_maxabs"] <= 1e-4, rep
+
+
+# ------------------------------------------------------------------------------------------------
+# opt-in treelet SAH optimisation (prt_treelet.cuh)
+@pytest.mark.parametrize("name", ["interior", "blob_incoherent", "soup_negative_t", "duplicates"])
+def test_treelet_optimisation_keeps_results_and_lowers_sah_cost(name, emu):
+    from bvhcheck import sah_internal_area
+    tris, rays = CASES[name]
+    emu.build(tris, 10)
+    before = emu.trace(rays)
+    n0, _ = emu.download()
+    cost = [sah_internal_area(n0)]
+    for p in range(3):
+        depth, changed = emu.treelet(1)
+        nodes, recs = emu.download()
+        assert check_bvh(nodes, recs, tris) == depth  # still a valid tree with exact boxes
+        cost.append(sah_internal_area(nodes))
+        assert cost[-1] <= cost[-2] * (1 + 1e-6), cost
+        assert depth <= 96
+    assert cost[1] < cost[0] * 0.98, cost
+    after = emu.trace(rays)
+    for k in ("valid", "t", "pid", "u", "v"):
+        assert np.array_equal(after[k], before[k], equal_nan=True), k
+    wide = emu.trace(rays, wide=True)  # the 4-wide view is rebuilt from the optimised tree
+    for k in ("valid", "t", "pid"):
+        assert np.array_equal(wide[k], before[k], equal_nan=True), k
+    print(name, "SAH internal area per pass", [round(c, 2) for c in cost], "boxes/ray",
+          before["counts"][:, 0].mean(), "->", after["counts"][:, 0].mean(),
+          "tris/ray", before["counts"][:, 1].mean(), "->", after["counts"][:, 1].mean())
+    if name == "interior":
+        assert after["counts"].sum() < before["counts"].sum()
