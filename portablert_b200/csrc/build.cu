@@ -462,41 +462,160 @@ __global__ void __launch_bounds__(256)
 		leaf_parent[~c1] = i;
 }
 
-// One thread per triangle climbs towards the root; at every internal node the first arrival
-// retires and the second one -- which therefore sees both finished subtrees -- optimises the
-// treelet rooted there (if at least TREELET_N triangles hang below) and carries on.  A treelet only
-// rewrites nodes inside the subtree of its root, which no other thread touches any more, and what
-// it writes depends only on that subtree: the result does not depend on arrival order.
-__global__ void __launch_bounds__(128)
+// The dynamic programme of one treelet spread over the 32 lanes of a warp (same recurrence and the
+// same tie rule as the sequential treelet_dp of prt_treelet.cuh, so the result is identical):
+// subset areas four per lane; subsets of 2..5 leaves one per lane; the 7 subsets of 6 leaves by 4
+// lanes each and the full set by all 32, merged with shuffles on the key (cost, half).
+struct TreeletShared {
+	Treelet t;
+	float area[TREELET_SETS], copt[TREELET_SETS];
+	uint8_t part[TREELET_SETS];
+};
+
+__device__ __forceinline__ void reduce_split(float &best, int &bp, int width) {
+	for (int o = 1; o < width; o <<= 1) {
+		const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+		const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+		if (ob < best || (ob == best && op < bp)) {
+			best = ob;
+			bp = op;
+		}
+	}
+}
+
+__device__ void treelet_optimise_warp(Node *nodes, int32_t x, int32_t *depth, TreeletShared &sh,
+                                      const uint8_t *by_size, const uint8_t *size_off,
+                                      unsigned lane) {
+	if (lane == 0)
+		treelet_form(nodes, x, depth, sh.t);
+	__syncwarp();
+	for (int s = lane; s < TREELET_SETS; s += 32) {
+		sh.area[s] = s ? treelet_subset_area(sh.t, s) : 0.0f;
+		if ((s & (s - 1)) == 0) {
+			sh.copt[s] = 0.0f;
+			sh.part[s] = 0;
+		}
+	}
+	__syncwarp();
+	for (int k = 2; k <= 5; ++k) {
+		for (int i = size_off[k] + lane; i < size_off[k + 1]; i += 32) {
+			const int s = by_size[i];
+			float best;
+			int bp;
+			treelet_best_split(sh.copt, s, 0, 1, best, bp);
+			sh.copt[s] = fadd(sh.area[s], best);
+			sh.part[s] = (uint8_t)(bp == 0xff ? treelet_first_split(s) : bp);
+		}
+		__syncwarp();
+	}
+	{ // 7 subsets of 6 leaves, 4 lanes each (lanes 28..31 idle)
+		const int which = lane >> 2;
+		const int s = which < TREELET_N ? by_size[size_off[6] + which] : 0;
+		float best = INFINITY;
+		int bp = 0xff;
+		if (s)
+			treelet_best_split(sh.copt, s, lane & 3, 4, best, bp);
+		reduce_split(best, bp, 4);
+		if (s && (lane & 3) == 0) {
+			sh.copt[s] = fadd(sh.area[s], best);
+			sh.part[s] = (uint8_t)(bp == 0xff ? treelet_first_split(s) : bp);
+		}
+	}
+	__syncwarp();
+	{ // the full set: 63 splits over 32 lanes
+		const int s = TREELET_SETS - 1;
+		float best;
+		int bp;
+		treelet_best_split(sh.copt, s, lane, 32, best, bp);
+		reduce_split(best, bp, 32);
+		if (lane == 0) {
+			sh.copt[s] = fadd(sh.area[s], best);
+			sh.part[s] = (uint8_t)(bp == 0xff ? treelet_first_split(s) : bp);
+		}
+	}
+	__syncwarp();
+	if (lane == 0) {
+		treelet_commit(nodes, sh.t, sh.area, sh.copt, sh.part, depth);
+		__threadfence(); // the lane that owns x publishes it to its parent's other subtree next round
+	}
+	__syncwarp();
+}
+
+// One lane per triangle climbs towards the root; at every internal node the first arrival retires
+// and the second one -- which therefore sees both finished subtrees -- has the treelet rooted
+// there optimised (if at least TREELET_N triangles hang below) and carries on.  The lanes of a
+// warp stay together: each round, the treelets its lanes have reached are optimised one after the
+// other by the whole warp.  A treelet only rewrites nodes inside the subtree of its root, which no
+// other warp touches any more, and what it writes depends only on that subtree: the result does
+// not depend on arrival order.
+constexpr int TL_THREADS = 128;
+__global__ void __launch_bounds__(TL_THREADS)
     k_treelet(Node *nodes, int n_tris, const int32_t *__restrict__ parent,
               const int32_t *__restrict__ leaf_parent, unsigned *flag, int32_t *count, int32_t *depth,
               RootInfo *root_info) {
+	__shared__ TreeletShared sh[TL_THREADS / 32];
+	__shared__ uint8_t by_size[TREELET_SETS], size_off[TREELET_N + 2];
+	{ // subsets ordered by their number of leaves (popcount, then value)
+		const int s = threadIdx.x;
+		if (s < TREELET_SETS) {
+			int pos = 0;
+			for (int q = 0; q < TREELET_SETS; ++q) {
+				const int a = __popc(q), b = __popc(s);
+				pos += (a < b || (a == b && q < s)) ? 1 : 0;
+			}
+			by_size[pos] = (uint8_t)s;
+		}
+		if (s <= TREELET_N + 1) {
+			int off = 0;
+			for (int q = 0; q < TREELET_SETS; ++q)
+				off += __popc(q) < s ? 1 : 0;
+			size_off[s] = (uint8_t)off; // (size_off[8] = 128 fits)
+		}
+	}
+	__syncthreads();
+	const unsigned lane = threadIdx.x & 31;
+	TreeletShared &mine = sh[threadIdx.x >> 5];
 	const int j = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-	if (j >= n_tris)
-		return;
 	const int32_t root = root_info->root;
-	int32_t cur = leaf_parent[j];
-	for (;;) {
-		__threadfence(); // release what this thread wrote below `cur`
-		if (atomicAdd(flag + cur, 1u) == 0u)
-			return;
-		__threadfence(); // acquire the sibling subtree
-		const int4 tail = __ldcg(reinterpret_cast<const int4 *>(nodes + cur) + 3);
-		const int32_t c0 = tail.x, c1 = tail.y;
-		const int32_t n0 = c0 < 0 ? 1 : __ldcg(count + c0), n1 = c1 < 0 ? 1 : __ldcg(count + c1);
-		const int32_t total = n0 + n1;
-		if (total >= TREELET_N) {
-			treelet_optimise(nodes, cur, depth);
-		} else {
-			const int32_t d0 = c0 < 0 ? 0 : __ldcg(depth + c0), d1 = c1 < 0 ? 0 : __ldcg(depth + c1);
-			depth[cur] = 1 + max(d0, d1);
+	bool alive = j < n_tris;
+	int32_t cur = alive ? leaf_parent[j] : 0;
+	while (__any_sync(0xffffffffu, alive)) {
+		bool need = false;
+		int32_t total = 0;
+		if (alive) {
+			__threadfence(); // release what this lane's warp wrote below `cur`
+			if (atomicAdd(flag + cur, 1u) == 0u) {
+				alive = false;
+			} else {
+				__threadfence(); // acquire the sibling subtree
+				const int4 tail = __ldcg(reinterpret_cast<const int4 *>(nodes + cur) + 3);
+				const int32_t c0 = tail.x, c1 = tail.y;
+				const int32_t n0 = c0 < 0 ? 1 : __ldcg(count + c0), n1 = c1 < 0 ? 1 : __ldcg(count + c1);
+				total = n0 + n1;
+				need = total >= TREELET_N;
+				if (!need) {
+					const int32_t d0 = c0 < 0 ? 0 : __ldcg(depth + c0);
+					const int32_t d1 = c1 < 0 ? 0 : __ldcg(depth + c1);
+					depth[cur] = 1 + max(d0, d1);
+				}
+			}
 		}
-		count[cur] = total;
-		if (cur == root) {
-			root_info->depth = depth[cur];
-			return;
+		unsigned todo = __ballot_sync(0xffffffffu, alive && need);
+		while (todo) {
+			const int src = __ffs(todo) - 1;
+			todo &= todo - 1;
+			const int32_t x = __shfl_sync(0xffffffffu, cur, src);
+			treelet_optimise_warp(nodes, x, depth, mine, by_size, size_off, lane);
 		}
-		cur = parent[cur];
+		if (alive) {
+			count[cur] = total;
+			if (cur == root) {
+				root_info->depth = __ldcg(depth + cur);
+				alive = false;
+			} else {
+				cur = parent[cur];
+			}
+		}
 	}
 }
 
@@ -643,7 +762,7 @@ int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 			k_parents<<<(int)((n - 1 + 255) / 256), 256, 0, s>>>(c->nodes.as<Node>(), (int)(n - 1),
 			                                                    c->tl_parent.as<int32_t>(),
 			                                                    c->tl_leaf_parent.as<int32_t>());
-			k_treelet<<<(int)((n + 127) / 128), 128, 0, s>>>(
+			k_treelet<<<(int)((n + TL_THREADS - 1) / TL_THREADS), TL_THREADS, 0, s>>>(
 			    c->nodes.as<Node>(), (int)n, c->tl_parent.as<int32_t>(), c->tl_leaf_parent.as<int32_t>(),
 			    c->tl_flag.as<unsigned>(), c->tl_count.as<int32_t>(), c->tl_depth.as<int32_t>(),
 			    c->root_info.as<RootInfo>());

@@ -77,99 +77,134 @@ PRT_HD void set_child(Node &nd, int side, int32_t ref, const Box &b) {
 	(side ? nd.child1 : nd.child0) = ref;
 }
 
-// Optimises the treelet rooted at internal node x (which must have >= TREELET_N leaves below it).
-// depth[i] = height of internal node i's subtree (a node over two triangles has height 1): read
-// for the subtrees hanging off the treelet, written for every node slot of the treelet, x included.
-// Returns true when the topology was replaced.
-PRT_HD bool treelet_optimise(Node *nodes, int32_t x, int32_t *depth) {
+// A treelet: TREELET_N subtrees ("leaves") hanging off TREELET_N-1 internal node slots.
+struct Treelet {
 	int32_t leaf_ref[TREELET_N];
 	Box leaf_box[TREELET_N];
 	float leaf_area[TREELET_N];
-	int32_t slot[TREELET_N - 1]; // node indices of the treelet's internal nodes, slot[0] = x
-	int n = 2, ns = 1;
-	float old_cost = 0.0f; // areas of the expanded nodes (the root's is added below)
+	int32_t leaf_depth[TREELET_N];
+	int32_t slot[TREELET_N - 1]; // node indices of the treelet's internal nodes, slot[0] = root
+	int32_t root_child[2];
+	int n;
+	float old_cost; // summed half areas of the expanded internal nodes (root excluded)
+};
 
+// Grow the treelet below x by always expanding the leaf with the largest surface area.
+PRT_HD void treelet_form(const Node *nodes, int32_t x, const int32_t *depth, Treelet &t) {
 	const Node root = treelet_load(nodes, x);
-	slot[0] = x;
-	leaf_ref[0] = root.child0;
-	leaf_ref[1] = root.child1;
-	leaf_box[0] = child_box(root, 0);
-	leaf_box[1] = child_box(root, 1);
-	leaf_area[0] = box_half_area(leaf_box[0]);
-	leaf_area[1] = box_half_area(leaf_box[1]);
+	int n = 2, ns = 1;
+	float old_cost = 0.0f;
+	t.slot[0] = x;
+	t.root_child[0] = root.child0;
+	t.root_child[1] = root.child1;
+	t.leaf_ref[0] = root.child0;
+	t.leaf_ref[1] = root.child1;
+	t.leaf_box[0] = child_box(root, 0);
+	t.leaf_box[1] = child_box(root, 1);
+	t.leaf_area[0] = box_half_area(t.leaf_box[0]);
+	t.leaf_area[1] = box_half_area(t.leaf_box[1]);
 	while (n < TREELET_N) {
 		int best = -1;
 		float best_area = -1.0f;
 		for (int k = 0; k < n; ++k)
-			if (leaf_ref[k] >= 0 && (best < 0 || leaf_area[k] > best_area)) {
+			if (t.leaf_ref[k] >= 0 && (best < 0 || t.leaf_area[k] > best_area)) {
 				best = k;
-				best_area = leaf_area[k];
+				best_area = t.leaf_area[k];
 			}
 		if (best < 0)
 			break; // (cannot happen with >= TREELET_N leaves below x)
-		const int32_t e = leaf_ref[best];
+		const int32_t e = t.leaf_ref[best];
 		const Node nd = treelet_load(nodes, e);
-		slot[ns++] = e;
-		old_cost = fadd(old_cost, leaf_area[best]);
-		leaf_ref[best] = nd.child0;
-		leaf_box[best] = child_box(nd, 0);
-		leaf_area[best] = box_half_area(leaf_box[best]);
-		leaf_ref[n] = nd.child1;
-		leaf_box[n] = child_box(nd, 1);
-		leaf_area[n] = box_half_area(leaf_box[n]);
+		t.slot[ns++] = e;
+		old_cost = fadd(old_cost, t.leaf_area[best]);
+		t.leaf_ref[best] = nd.child0;
+		t.leaf_box[best] = child_box(nd, 0);
+		t.leaf_area[best] = box_half_area(t.leaf_box[best]);
+		t.leaf_ref[n] = nd.child1;
+		t.leaf_box[n] = child_box(nd, 1);
+		t.leaf_area[n] = box_half_area(t.leaf_box[n]);
 		++n;
 	}
-	int32_t leaf_depth[TREELET_N];
 	for (int k = 0; k < n; ++k)
-		leaf_depth[k] = leaf_ref[k] < 0 ? 0 : treelet_load_i32(depth + leaf_ref[k]);
+		t.leaf_depth[k] = t.leaf_ref[k] < 0 ? 0 : treelet_load_i32(depth + t.leaf_ref[k]);
+	t.n = n;
+	t.old_cost = old_cost;
+}
 
-	// ---- dynamic programming over the subsets of the leaves
-	const int full = (1 << n) - 1;
-	float area[TREELET_SETS], copt[TREELET_SETS];
-	uint8_t part[TREELET_SETS];
-	for (int s = 1; s <= full; ++s) {
-		Box b;
-		bool first = true;
-		for (int k = 0; k < n; ++k)
-			if (s & (1 << k)) {
-				b = first ? leaf_box[k] : box_union(b, leaf_box[k]);
-				first = false;
-			}
-		area[s] = box_half_area(b);
-	}
-	for (int s = 1; s <= full; ++s) {
-		if ((s & (s - 1)) == 0) { // a single leaf: nothing to arrange
-			copt[s] = 0.0f;
-			part[s] = 0;
-			continue;
+PRT_HD float treelet_subset_area(const Treelet &t, int s) {
+	Box b;
+	bool first = true;
+	for (int k = 0; k < t.n; ++k)
+		if (s & (1 << k)) {
+			b = first ? t.leaf_box[k] : box_union(b, t.leaf_box[k]);
+			first = false;
 		}
-		// all ways to split s in two non-empty halves; the half holding s's lowest bit is the complement
-		const int delta = (s - 1) & s;
-		int p = (-delta) & s;
-		float best = INFINITY;
-		int bp = p;
-		do {
+	return box_half_area(b);
+}
+
+// Best split of subset s (>= 2 leaves) into two non-empty halves, given copt of all its proper
+// subsets: minimum cost, and among equal costs the numerically smallest half p (the enumeration
+// runs through the non-empty subsets of s-without-its-lowest-bit in increasing order).  Lanes of
+// a warp may share one subset: lane `sub` of `nsub` takes every nsub-th candidate.
+PRT_HD void treelet_best_split(const float *copt, int s, int sub, int nsub, float &best, int &bp) {
+	const int delta = (s - 1) & s;
+	int p = (-delta) & s;
+	int i = 0;
+	best = INFINITY;
+	bp = 0xff; // none found (all candidates infinite or NaN): the caller falls back to the first
+	do {
+		if (nsub == 1 || (i % nsub) == sub) {
 			const float c = fadd(copt[p], copt[s ^ p]);
 			if (c < best) {
 				best = c;
 				bp = p;
 			}
-			p = (p - delta) & s;
-		} while (p != 0);
-		copt[s] = fadd(area[s], best);
-		part[s] = (uint8_t)bp;
-	}
-	old_cost = fadd(old_cost, area[full]);
+		}
+		++i;
+		p = (p - delta) & s;
+	} while (p != 0);
+}
 
-	if (!(copt[full] < old_cost)) {
-		// keep the topology; x's height follows from its two children
-		const int32_t d0 = root.child0 < 0 ? 0 : treelet_load_i32(depth + root.child0);
-		const int32_t d1 = root.child1 < 0 ? 0 : treelet_load_i32(depth + root.child1);
+PRT_HD int treelet_first_split(int s) {
+	const int delta = (s - 1) & s;
+	return (-delta) & s;
+}
+
+// Sequential dynamic programme over all subsets (host emulator; the device kernel spreads the same
+// recurrence over the lanes of a warp, build.cu).
+PRT_HD void treelet_dp(const Treelet &t, float *area, float *copt, uint8_t *part) {
+	const int full = (1 << t.n) - 1;
+	for (int s = 1; s <= full; ++s)
+		area[s] = treelet_subset_area(t, s);
+	for (int s = 1; s <= full; ++s) { // every proper subset of s is numerically smaller than s
+		if ((s & (s - 1)) == 0) {     // a single leaf: nothing to arrange
+			copt[s] = 0.0f;
+			part[s] = 0;
+			continue;
+		}
+		float best;
+		int bp;
+		treelet_best_split(copt, s, 0, 1, best, bp);
+		copt[s] = fadd(area[s], best);
+		part[s] = (uint8_t)(bp == 0xff ? treelet_first_split(s) : bp);
+	}
+}
+
+// Replace the treelet's topology by the optimal one if that lowers the summed area; set depth[]
+// of every node slot written (or of the root alone when the topology stays).  Returns true when
+// the topology was replaced.
+PRT_HD bool treelet_commit(Node *nodes, const Treelet &t, const float *area, const float *copt,
+                           const uint8_t *part, int32_t *depth) {
+	const int n = t.n, full = (1 << n) - 1;
+	const int32_t x = t.slot[0];
+	if (!(copt[full] < fadd(t.old_cost, area[full]))) {
+		const int32_t c0 = t.root_child[0], c1 = t.root_child[1];
+		const int32_t d0 = c0 < 0 ? 0 : treelet_load_i32(depth + c0);
+		const int32_t d1 = c1 < 0 ? 0 : treelet_load_i32(depth + c1);
 		depth[x] = 1 + (d0 > d1 ? d0 : d1);
 		return false;
 	}
-
-	// ---- write the optimal topology back into the same node slots (parents before children)
+	// parents before children: slot k's children take the next free slots
 	uint8_t todo_set[TREELET_N - 1];
 	int8_t kid[TREELET_N - 1][2]; // >= 0: slot number, < 0: ~leaf number
 	todo_set[0] = (uint8_t)full;
@@ -186,31 +221,43 @@ PRT_HD bool treelet_optimise(Node *nodes, int32_t x, int32_t *depth) {
 			int only = -1;
 			for (int j = 0; j < n; ++j)
 				if (h & (1 << j)) {
-					b = first ? leaf_box[j] : box_union(b, leaf_box[j]);
+					b = first ? t.leaf_box[j] : box_union(b, t.leaf_box[j]);
 					first = false;
 					only = j;
 				}
 			if ((h & (h - 1)) == 0) {
-				set_child(nd, side, leaf_ref[only], b);
+				set_child(nd, side, t.leaf_ref[only], b);
 				kid[k][side] = (int8_t)~only;
 			} else {
 				todo_set[used] = (uint8_t)h;
-				set_child(nd, side, slot[used], b);
+				set_child(nd, side, t.slot[used], b);
 				kid[k][side] = (int8_t)used;
 				++used;
 			}
 		}
-		treelet_store(nodes, slot[k], nd);
+		treelet_store(nodes, t.slot[k], nd);
 	}
 	int32_t slot_depth[TREELET_N - 1];
 	for (int k = used - 1; k >= 0; --k) {
 		int32_t d[2];
 		for (int side = 0; side < 2; ++side)
-			d[side] = kid[k][side] < 0 ? leaf_depth[~kid[k][side]] : slot_depth[kid[k][side]];
+			d[side] = kid[k][side] < 0 ? t.leaf_depth[~kid[k][side]] : slot_depth[kid[k][side]];
 		slot_depth[k] = 1 + (d[0] > d[1] ? d[0] : d[1]);
-		depth[slot[k]] = slot_depth[k];
+		depth[t.slot[k]] = slot_depth[k];
 	}
 	return true;
+}
+
+// Optimises the treelet rooted at internal node x (which must have >= TREELET_N leaves below it).
+// depth[i] = height of internal node i's subtree (a node over two triangles has height 1): read
+// for the subtrees hanging off the treelet, written for every node slot of the treelet, x included.
+PRT_HD bool treelet_optimise(Node *nodes, int32_t x, int32_t *depth) {
+	Treelet t;
+	float area[TREELET_SETS], copt[TREELET_SETS];
+	uint8_t part[TREELET_SETS];
+	treelet_form(nodes, x, depth, t);
+	treelet_dp(t, area, copt, part);
+	return treelet_commit(nodes, t, area, copt, part, depth);
 }
 
 } // namespace prt
