@@ -127,15 +127,22 @@ int prt_b200_trace_dev_aos(prt_b200 *ctx, const float *d_rays6, uint64_t n_rays,
 /* Traversal knobs; opts == NULL restores the defaults. */
 int prt_b200_set_trace_opts(prt_b200 *ctx, const prt_trace_opts *opts);
 
-/* Opt-in SAH optimisation of the LBVH inside set_tris: `passes` bottom-up rounds of treelet
- * restructuring (Karras & Aila 2013: 7-leaf treelets, exact dynamic programming over their
- * topologies, minimising the summed surface area of the internal nodes -- the quantity the
- * reference's binned SAH sweep, bvh.hpp:58-129, greedily minimises top-down).  0 = off (default:
- * fastest build); env PRT_B200_TREELET.  Results of nearest_hits do not depend on it, only the
- * number of boxes visited per ray.  Takes effect at the next set_tris.  prt_b200_tree_depth: height
- * of the optimised tree (0 when the pass did not run). */
-int prt_b200_set_treelet_passes(prt_b200 *ctx, int passes);
+/* SAH optimisation of the LBVH: `passes` bottom-up rounds of treelet restructuring (Karras & Aila
+ * 2013: 7-leaf treelets, exact dynamic programming over their topologies, minimising the summed
+ * surface area of the internal nodes -- the quantity the reference's binned SAH sweep,
+ * bvh.hpp:58-129, minimises greedily top-down).  Results of nearest_hits do not depend on it, only
+ * the number of boxes visited per ray (measured: -6 % on C2, -46 % on the C3 interior).
+ *   mode 0  never: set_tris leaves the radix tree as built (fastest build)
+ *   mode 1  inside every set_tris
+ *   mode 2  (default) lazily: once a scene has been asked for 16 rays per triangle -- about what the
+ *           optimisation costs -- it is optimised before the next batch is traced; a scene rebuilt
+ *           every frame (config C5) never pays for it, a static one pays once
+ * passes: 1..8 (default 2).  Env PRT_B200_TREELET_MODE / PRT_B200_TREELET_PASSES.
+ * prt_b200_tree_depth: height of the optimised tree (0 = the current tree is the plain radix tree);
+ * prt_b200_last_optimise_ms: device time the lazy optimisation of the current scene took. */
+int prt_b200_set_tree_optimisation(prt_b200 *ctx, int mode, int passes);
 int32_t prt_b200_tree_depth(const prt_b200 *ctx);
+float prt_b200_last_optimise_ms(const prt_b200 *ctx);
 
 /* Triangle test: 0 (default) = the reference's Moeller-Trumbore arithmetic replayed operation for
  * operation (core.hpp:27-65) -- results identical to the reference CPU backend; 1 = opt-in

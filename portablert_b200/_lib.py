@@ -45,8 +45,9 @@ SYMBOLS = {
     "prt_b200_trace_dev_aos": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
                                          C.POINTER(HitLayout), C.c_void_p, C.POINTER(C.c_float)]),
     "prt_b200_set_trace_opts": (C.c_int, [C.c_void_p, C.POINTER(TraceOpts)]),
-    "prt_b200_set_treelet_passes": (C.c_int, [C.c_void_p, C.c_int]),
+    "prt_b200_set_tree_optimisation": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "prt_b200_tree_depth": (C.c_int32, [C.c_void_p]),
+    "prt_b200_last_optimise_ms": (C.c_float, [C.c_void_p]),
     "prt_b200_set_triangle_test": (C.c_int, [C.c_void_p, C.c_int]),
     "prt_b200_triangle_test": (C.c_int, [C.c_void_p]),
     "prt_b200_set_ray_sorting": (C.c_int, [C.c_void_p, C.c_int]),

@@ -159,16 +159,22 @@ class CUDABackend(Backend):
         self._need()
         self._check(lib().prt_b200_set_ray_sorting(self._h, int(mode)))
 
-    def set_treelet_passes(self, passes: int):
-        """Opt-in SAH optimisation of the tree inside set_tris (treelet restructuring, Karras & Aila
-        2013); 0 = off (default).  Applies from the next set_tris."""
+    def set_tree_optimisation(self, mode: int, passes: int = 2):
+        """SAH optimisation of the LBVH by treelet restructuring (Karras & Aila 2013): mode 0 never,
+        1 inside every set_tris, 2 (default) lazily once a scene has served 16 rays per triangle."""
         self._need()
-        self._check(lib().prt_b200_set_treelet_passes(self._h, int(passes)))
+        self._check(lib().prt_b200_set_tree_optimisation(self._h, int(mode), int(passes)))
 
     @property
     def tree_depth(self) -> int:
+        """height of the optimised tree; 0 while the current tree is the plain radix tree"""
         self._need()
         return int(lib().prt_b200_tree_depth(self._h))
+
+    @property
+    def last_optimise_ms(self) -> float:
+        self._need()
+        return float(lib().prt_b200_last_optimise_ms(self._h))
 
     def set_triangle_test(self, mode: int):
         """0 (default): the reference's Moeller-Trumbore arithmetic (core.hpp:27-65), results identical

@@ -141,8 +141,10 @@ int prt_b200_create(prt_b200 **out, int device) {
 	c->sm_count = prop.multiProcessorCount;
 	if (const char *e = std::getenv("PRT_B200_FAST_BOXES"))
 		c->fast_boxes = std::atoi(e) != 0;
-	if (const char *e = std::getenv("PRT_B200_TREELET"))
-		c->treelet_passes = std::max(0, std::min(8, std::atoi(e)));
+	if (const char *e = std::getenv("PRT_B200_TREELET_MODE"))
+		c->optimise_mode = std::max(0, std::min(2, std::atoi(e)));
+	if (const char *e = std::getenv("PRT_B200_TREELET_PASSES"))
+		c->optimise_passes = std::max(1, std::min(8, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_WATERTIGHT"))
 		c->watertight = std::atoi(e) != 0;
 	if (const char *e = std::getenv("PRT_B200_WIDE"))
@@ -219,13 +221,15 @@ int prt_b200_set_wide_nodes(prt_b200 *c, int mode) {
 	return PRT_OK;
 }
 
-int prt_b200_set_treelet_passes(prt_b200 *c, int passes) {
-	if (!c || passes < 0 || passes > 8)
-		return fail(c, PRT_E_ARG, "set_treelet_passes: passes must be in 0..8");
-	c->treelet_passes = passes;
+int prt_b200_set_tree_optimisation(prt_b200 *c, int mode, int passes) {
+	if (!c || mode < 0 || mode > 2 || passes < 1 || passes > 8)
+		return fail(c, PRT_E_ARG, "set_tree_optimisation: mode must be 0..2 and passes 1..8");
+	c->optimise_mode = mode;
+	c->optimise_passes = passes;
 	return PRT_OK;
 }
 int32_t prt_b200_tree_depth(const prt_b200 *c) { return c ? c->tree_depth : 0; }
+float prt_b200_last_optimise_ms(const prt_b200 *c) { return c ? c->last_optimise_ms : 0.f; }
 
 int prt_b200_set_triangle_test(prt_b200 *c, int mode) {
 	if (!c || mode < 0 || mode > 1)
@@ -270,15 +274,6 @@ static int timed_build(prt_b200 *c, const float *d_tris9, uint64_t n, float *ms)
 		PRT_CUDA(c, cudaMemcpyAsync(&ri, c->root_info.p, sizeof ri, cudaMemcpyDeviceToHost, c->stream));
 	PRT_CUDA(c, cudaStreamSynchronize(c->stream));
 	PRT_CUDA(c, cudaEventElapsedTime(&c->last_build_ms, c->ev0, c->ev1));
-	// The traversal stack is sized for the radix tree's depth bound (prt_traverse.cuh); treelet
-	// restructuring has no such bound, so a tree that came out deeper is rebuilt without it.
-	c->tree_depth = c->n_nodes ? ri.depth : 0;
-	if (c->tree_depth > 96 && !c->treelet_suspended) {
-		c->treelet_suspended = true;
-		rc = timed_build(c, d_tris9, n, ms);
-		c->treelet_suspended = false;
-		return rc;
-	}
 	c->root = c->n_nodes ? ri.root : 0;
 	for (int a = 0; a < 3; ++a) {
 		c->scene_lo[a] = c->n_nodes ? ri.lo[a] : 0.f;
@@ -356,6 +351,8 @@ int prt_b200_trace_dev(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t m
 	          ((mask & PRT_TAG_PID) && !o->pid) || ((mask & PRT_TAG_P) && !o->p) ||
 	          ((mask & PRT_TAG_VALID) && !o->valid)))
 		return fail(c, PRT_E_ARG, "trace_dev: NULL output for a requested tag");
+	if (int rc = prt::maybe_optimise_tree(c, n))
+		return rc;
 	prt::TraceOut out;
 	out.soa = *o;
 	return timed_trace(c, d_rays6, n, mask, out, nullptr, trace_ms);
@@ -368,6 +365,8 @@ int prt_b200_trace_dev_aos(prt_b200 *c, const float *d_rays6, uint64_t n, uint32
 	if (mask == 0 || mask > PRT_TAG_ALL)
 		return fail(c, PRT_E_ARG, "trace_dev_aos: tag mask must be in 1..31");
 	if (int rc = check_layout(c, mask, layout))
+		return rc;
+	if (int rc = prt::maybe_optimise_tree(c, n))
 		return rc;
 	prt::TraceOut out;
 	out.aos = d_hits;
@@ -438,6 +437,8 @@ int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t 
 	if (n == 0)
 		return PRT_OK;
 	PRT_CUDA(c, cudaSetDevice(c->device));
+	if (int rc = prt::maybe_optimise_tree(c, n))
+		return rc;
 
 	const bool in_pinned = is_pinned(rays6), out_pinned = is_pinned(hits_out);
 	// Chunk schedule: the D2H engine is the bottleneck (records are larger than rays) and starts

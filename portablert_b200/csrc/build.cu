@@ -485,7 +485,7 @@ __device__ __forceinline__ void reduce_split(float &best, int &bp, int width) {
 
 __device__ void treelet_optimise_warp(Node *nodes, int32_t x, int32_t *depth, TreeletShared &sh,
                                       const uint8_t *by_size, const uint8_t *size_off,
-                                      unsigned lane) {
+                                      unsigned lane, bool strict) {
 	if (lane == 0)
 		treelet_form(nodes, x, depth, sh.t);
 	__syncwarp();
@@ -535,7 +535,7 @@ __device__ void treelet_optimise_warp(Node *nodes, int32_t x, int32_t *depth, Tr
 	}
 	__syncwarp();
 	if (lane == 0) {
-		treelet_commit(nodes, sh.t, sh.area, sh.copt, sh.part, depth);
+		treelet_commit(nodes, sh.t, sh.area, sh.copt, sh.part, depth, strict);
 		__threadfence(); // the lane that owns x publishes it to its parent's other subtree next round
 	}
 	__syncwarp();
@@ -552,7 +552,7 @@ constexpr int TL_THREADS = 128;
 __global__ void __launch_bounds__(TL_THREADS)
     k_treelet(Node *nodes, int n_tris, const int32_t *__restrict__ parent,
               const int32_t *__restrict__ leaf_parent, unsigned *flag, int32_t *count, int32_t *depth,
-              RootInfo *root_info) {
+              RootInfo *root_info, bool strict) {
 	__shared__ TreeletShared sh[TL_THREADS / 32];
 	__shared__ uint8_t by_size[TREELET_SETS], size_off[TREELET_N + 2];
 	{ // subsets ordered by their number of leaves (popcount, then value)
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(TL_THREADS)
 			const int src = __ffs(todo) - 1;
 			todo &= todo - 1;
 			const int32_t x = __shfl_sync(0xffffffffu, cur, src);
-			treelet_optimise_warp(nodes, x, depth, mine, by_size, size_off, lane);
+			treelet_optimise_warp(nodes, x, depth, mine, by_size, size_off, lane, strict);
 		}
 		if (alive) {
 			count[cur] = total;
@@ -679,6 +679,90 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------------
+static int build_wide(prt_b200 *c, cudaStream_t s) {
+	if (!c->wide_built || c->n_nodes == 0)
+		return PRT_OK;
+	PRT_CUDA(c, c->nodes4.reserve(c->n_nodes * sizeof(Node4)));
+	k_wide<<<(int)((c->n_nodes + 255) / 256), 256, 0, s>>>(c->nodes.as<Node>(), (int)c->n_nodes,
+	                                                      c->nodes4.as<Node4>());
+	c->launches += 1;
+	return PRT_OK;
+}
+
+static int treelet_passes(prt_b200 *c, cudaStream_t s, int passes, bool strict) {
+	const uint64_t n = c->n_tris;
+	for (int pass = 0; pass < passes; ++pass) {
+		PRT_CUDA(c, cudaMemsetAsync(c->tl_flag.p, 0, (n - 1) * 4, s));
+		k_parents<<<(int)((n - 1 + 255) / 256), 256, 0, s>>>(c->nodes.as<Node>(), (int)(n - 1),
+		                                                    c->tl_parent.as<int32_t>(),
+		                                                    c->tl_leaf_parent.as<int32_t>());
+		k_treelet<<<(int)((n + TL_THREADS - 1) / TL_THREADS), TL_THREADS, 0, s>>>(
+		    c->nodes.as<Node>(), (int)n, c->tl_parent.as<int32_t>(), c->tl_leaf_parent.as<int32_t>(),
+		    c->tl_flag.as<unsigned>(), c->tl_count.as<int32_t>(), c->tl_depth.as<int32_t>(),
+		    c->root_info.as<RootInfo>(), strict);
+		c->launches += 2;
+	}
+	PRT_CUDA(c, cudaGetLastError());
+	return PRT_OK;
+}
+
+// SAH optimisation of the current tree, in place (5b).  The restructured tree is measured: should it
+// come out taller than the traversal stack is sized for, the saved radix tree is restored and
+// optimised again under the height-preserving rule (treelet_commit: strict).  Synchronises `s`.
+int optimise_tree(prt_b200 *c, cudaStream_t s) {
+	const uint64_t n = c->n_tris;
+	if (n < (uint64_t)TREELET_N || c->optimise_passes < 1)
+		return PRT_OK;
+	PRT_CUDA(c, c->tl_parent.reserve((n - 1) * 4));
+	PRT_CUDA(c, c->tl_leaf_parent.reserve(n * 4));
+	PRT_CUDA(c, c->tl_flag.reserve((n - 1) * 4));
+	PRT_CUDA(c, c->tl_count.reserve((n - 1) * 4));
+	PRT_CUDA(c, c->tl_depth.reserve((n - 1) * 4));
+	PRT_CUDA(c, c->tl_backup.reserve((n - 1) * sizeof(Node)));
+	PRT_CUDA(c, cudaMemcpyAsync(c->tl_backup.p, c->nodes.p, (n - 1) * sizeof(Node),
+	                            cudaMemcpyDeviceToDevice, s));
+	int32_t depth = 0;
+	const char *depth_src = static_cast<const char *>(c->root_info.p) + offsetof(RootInfo, depth);
+	if (int rc = treelet_passes(c, s, c->optimise_passes, false))
+		return rc;
+	PRT_CUDA(c, cudaMemcpyAsync(&depth, depth_src, 4, cudaMemcpyDeviceToHost, s));
+	PRT_CUDA(c, cudaStreamSynchronize(s));
+	if (depth > MAX_TREE_DEPTH) {
+		PRT_CUDA(c, cudaMemcpyAsync(c->nodes.p, c->tl_backup.p, (n - 1) * sizeof(Node),
+		                            cudaMemcpyDeviceToDevice, s));
+		if (int rc = treelet_passes(c, s, c->optimise_passes, true))
+			return rc;
+		PRT_CUDA(c, cudaMemcpyAsync(&depth, depth_src, 4, cudaMemcpyDeviceToHost, s));
+		PRT_CUDA(c, cudaStreamSynchronize(s));
+		c->strict_fallbacks++;
+	}
+	c->tree_depth = depth;
+	c->tree_optimised = true;
+	return PRT_OK;
+}
+
+// Lazy mode (the default): a scene that keeps being traced is optimised once it has been asked for
+// LAZY_RAYS_PER_TRI rays per triangle -- about what the optimisation costs in traversal time --
+// so a per-frame rebuild (config C5: 8 rays per triangle and frame) never pays for it while a
+// static scene gets the better tree from its first or second batch on.  Called by the trace entry
+// points (api.cu) before they launch anything.
+int maybe_optimise_tree(prt_b200 *c, uint64_t n_rays) {
+	c->rays_since_build += n_rays;
+	if (c->optimise_mode != 2 || c->tree_optimised || c->n_tris < (uint64_t)TREELET_N ||
+	    c->rays_since_build < LAZY_RAYS_PER_TRI * c->n_tris)
+		return PRT_OK;
+	cudaStream_t s = c->stream;
+	PRT_CUDA(c, cudaEventRecord(c->ev0, s));
+	if (int rc = optimise_tree(c, s))
+		return rc;
+	if (int rc = build_wide(c, s))
+		return rc;
+	PRT_CUDA(c, cudaEventRecord(c->ev1, s));
+	PRT_CUDA(c, cudaStreamSynchronize(s));
+	PRT_CUDA(c, cudaEventElapsedTime(&c->last_optimise_ms, c->ev0, c->ev1));
+	return PRT_OK;
+}
+
 static int morton_bits_for(uint64_t n) {
 	if (const char *e = std::getenv("PRT_B200_MORTON_BITS")) { // experiments: 1..21 bits per axis
 		const int b = std::atoi(e);
@@ -701,6 +785,10 @@ int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 	c->n_tris = n;
 	c->n_nodes = n == 0 ? 0 : (n == 1 ? 1 : n - 1);
 	c->wide_built = false;
+	c->tree_optimised = false;
+	c->tree_depth = 0;
+	c->rays_since_build = 0;
+	c->last_optimise_ms = 0.f;
 	c->recs_vertex_form = c->watertight != 0;
 	const bool vf = c->recs_vertex_form;
 	if (n == 0)
@@ -750,32 +838,12 @@ int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 		                              c->bound.as<int>(), c->root_info.as<RootInfo>(), vf);
 		c->launches += 1;
 	}
-	// opt-in SAH optimisation of the tree just built (env PRT_B200_TREELET = number of passes)
-	if (c->treelet_passes > 0 && !c->treelet_suspended && n >= (uint64_t)TREELET_N) {
-		PRT_CUDA(c, c->tl_parent.reserve((n - 1) * 4));
-		PRT_CUDA(c, c->tl_leaf_parent.reserve(n * 4));
-		PRT_CUDA(c, c->tl_flag.reserve((n - 1) * 4));
-		PRT_CUDA(c, c->tl_count.reserve((n - 1) * 4));
-		PRT_CUDA(c, c->tl_depth.reserve((n - 1) * 4));
-		for (int pass = 0; pass < c->treelet_passes; ++pass) {
-			PRT_CUDA(c, cudaMemsetAsync(c->tl_flag.p, 0, (n - 1) * 4, s));
-			k_parents<<<(int)((n - 1 + 255) / 256), 256, 0, s>>>(c->nodes.as<Node>(), (int)(n - 1),
-			                                                    c->tl_parent.as<int32_t>(),
-			                                                    c->tl_leaf_parent.as<int32_t>());
-			k_treelet<<<(int)((n + TL_THREADS - 1) / TL_THREADS), TL_THREADS, 0, s>>>(
-			    c->nodes.as<Node>(), (int)n, c->tl_parent.as<int32_t>(), c->tl_leaf_parent.as<int32_t>(),
-			    c->tl_flag.as<unsigned>(), c->tl_count.as<int32_t>(), c->tl_depth.as<int32_t>(),
-			    c->root_info.as<RootInfo>());
-			c->launches += 2;
-		}
-	}
+	if (c->optimise_mode == 1) // inside every set_tris
+		if (int rc = optimise_tree(c, s))
+			return rc;
 	c->wide_built = !vf && (c->wide_mode == 1 || (c->wide_mode == 2 && n >= (1ull << 20)));
-	if (c->wide_built) {
-		PRT_CUDA(c, c->nodes4.reserve(c->n_nodes * sizeof(Node4)));
-		k_wide<<<(int)((c->n_nodes + 255) / 256), 256, 0, s>>>(c->nodes.as<Node>(), (int)c->n_nodes,
-		                                                      c->nodes4.as<Node4>());
-		c->launches += 1;
-	}
+	if (int rc = build_wide(c, s))
+		return rc;
 	PRT_CUDA(c, cudaGetLastError());
 	return PRT_OK;
 }

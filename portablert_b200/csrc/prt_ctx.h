@@ -90,10 +90,13 @@ struct prt_b200 {
 	// build scratch
 	prt::DevBuf keys[2], vals[2], sort_scratch, bounds, leaf_box, bound, root_info;
 	// opt-in treelet SAH optimisation (build.cu 5b): parent links, arrival flags, leaf counts, heights
-	prt::DevBuf tl_parent, tl_leaf_parent, tl_flag, tl_count, tl_depth;
-	int treelet_passes = 0;         // env PRT_B200_TREELET / prt_b200_set_treelet_passes: 0 = off (default)
-	bool treelet_suspended = false; // the optimised tree got deeper than the traversal stack allows
-	int32_t tree_depth = 0;         // height of the optimised tree (0 = not measured)
+	prt::DevBuf tl_parent, tl_leaf_parent, tl_flag, tl_count, tl_depth, tl_backup;
+	int optimise_mode = 2;   // env PRT_B200_TREELET_MODE: 0 never, 1 inside set_tris, 2 lazily (default)
+	int optimise_passes = 2; // env PRT_B200_TREELET_PASSES
+	bool tree_optimised = false;
+	uint64_t rays_since_build = 0, strict_fallbacks = 0;
+	float last_optimise_ms = 0.f; // device time of the lazy optimisation of the current scene (0 = none yet)
+	int32_t tree_depth = 0;       // height of the optimised tree (0 = not optimised)
 	int32_t root = 0; // index of the root node (the radix tree numbers nodes by split position)
 
 	// trace scratch
@@ -146,7 +149,11 @@ inline int fail(prt_b200 *c, int code, const char *what, cudaError_t e = cudaSuc
 	} while (0)
 
 // build.cu
+constexpr int MAX_TREE_DEPTH = 96;          // what prt_traverse.cuh: STACK_DEPTH is sized for
+constexpr uint64_t LAZY_RAYS_PER_TRI = 16;  // lazy tree optimisation threshold
 int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n);
+int optimise_tree(prt_b200 *c, cudaStream_t s);
+int maybe_optimise_tree(prt_b200 *c, uint64_t n_rays);
 // trace.cu
 struct TraceOut {
 	// SoA (aos == nullptr) or AoS (aos != nullptr)

@@ -190,20 +190,26 @@ PRT_HD void treelet_dp(const Treelet &t, float *area, float *copt, uint8_t *part
 	}
 }
 
-// Replace the treelet's topology by the optimal one if that lowers the summed area; set depth[]
+// Replace the treelet's topology by the optimal one if that lowers the summed area.  Sets depth[]
 // of every node slot written (or of the root alone when the topology stays).  Returns true when
 // the topology was replaced.
+// `strict`: additionally refuse a topology that makes the subtree of x taller than it is.  By
+// induction over the bottom-up order every subtree then stays at most as tall as in the radix tree,
+// whose height is bounded by the key length -- the bound the traversal stack is sized for
+// (prt_traverse.cuh: STACK_DEPTH).  It costs quality (big triangles want to sit high up, in a
+// locally deeper tree), so the build first runs without it, measures the height of the result and
+// only falls back to the strict rule if that exceeds the bound (build.cu: optimise_tree).
 PRT_HD bool treelet_commit(Node *nodes, const Treelet &t, const float *area, const float *copt,
-                           const uint8_t *part, int32_t *depth) {
+                           const uint8_t *part, int32_t *depth, bool strict) {
 	const int n = t.n, full = (1 << n) - 1;
 	const int32_t x = t.slot[0];
-	if (!(copt[full] < fadd(t.old_cost, area[full]))) {
-		const int32_t c0 = t.root_child[0], c1 = t.root_child[1];
-		const int32_t d0 = c0 < 0 ? 0 : treelet_load_i32(depth + c0);
-		const int32_t d1 = c1 < 0 ? 0 : treelet_load_i32(depth + c1);
-		depth[x] = 1 + (d0 > d1 ? d0 : d1);
+	const int32_t c0 = t.root_child[0], c1 = t.root_child[1];
+	const int32_t d0 = c0 < 0 ? 0 : treelet_load_i32(depth + c0);
+	const int32_t d1 = c1 < 0 ? 0 : treelet_load_i32(depth + c1);
+	const int32_t old_depth = 1 + (d0 > d1 ? d0 : d1);
+	depth[x] = old_depth;
+	if (!(copt[full] < fadd(t.old_cost, area[full])))
 		return false;
-	}
 	// parents before children: slot k's children take the next free slots
 	uint8_t todo_set[TREELET_N - 1];
 	int8_t kid[TREELET_N - 1][2]; // >= 0: slot number, < 0: ~leaf number
@@ -212,30 +218,19 @@ PRT_HD bool treelet_commit(Node *nodes, const Treelet &t, const float *area, con
 	for (int k = 0; k < used; ++k) {
 		const int s = todo_set[k];
 		const int half[2] = {part[s], s ^ part[s]};
-		Node nd;
-		nd.pad0 = nd.pad1 = 0;
 		for (int side = 0; side < 2; ++side) {
 			const int h = half[side];
-			Box b;
-			bool first = true;
-			int only = -1;
-			for (int j = 0; j < n; ++j)
-				if (h & (1 << j)) {
-					b = first ? t.leaf_box[j] : box_union(b, t.leaf_box[j]);
-					first = false;
-					only = j;
-				}
 			if ((h & (h - 1)) == 0) {
-				set_child(nd, side, t.leaf_ref[only], b);
+				int only = 0;
+				while (!(h & (1 << only)))
+					++only;
 				kid[k][side] = (int8_t)~only;
 			} else {
 				todo_set[used] = (uint8_t)h;
-				set_child(nd, side, t.slot[used], b);
 				kid[k][side] = (int8_t)used;
 				++used;
 			}
 		}
-		treelet_store(nodes, t.slot[k], nd);
 	}
 	int32_t slot_depth[TREELET_N - 1];
 	for (int k = used - 1; k >= 0; --k) {
@@ -243,6 +238,25 @@ PRT_HD bool treelet_commit(Node *nodes, const Treelet &t, const float *area, con
 		for (int side = 0; side < 2; ++side)
 			d[side] = kid[k][side] < 0 ? t.leaf_depth[~kid[k][side]] : slot_depth[kid[k][side]];
 		slot_depth[k] = 1 + (d[0] > d[1] ? d[0] : d[1]);
+	}
+	if (strict && slot_depth[0] > old_depth)
+		return false;
+	for (int k = 0; k < used; ++k) {
+		const int s = todo_set[k];
+		const int half[2] = {part[s], s ^ part[s]};
+		Node nd;
+		nd.pad0 = nd.pad1 = 0;
+		for (int side = 0; side < 2; ++side) {
+			Box b;
+			bool first = true;
+			for (int j = 0; j < n; ++j)
+				if (half[side] & (1 << j)) {
+					b = first ? t.leaf_box[j] : box_union(b, t.leaf_box[j]);
+					first = false;
+				}
+			set_child(nd, side, kid[k][side] < 0 ? t.leaf_ref[~kid[k][side]] : t.slot[kid[k][side]], b);
+		}
+		treelet_store(nodes, t.slot[k], nd);
 		depth[t.slot[k]] = slot_depth[k];
 	}
 	return true;
@@ -251,13 +265,13 @@ PRT_HD bool treelet_commit(Node *nodes, const Treelet &t, const float *area, con
 // Optimises the treelet rooted at internal node x (which must have >= TREELET_N leaves below it).
 // depth[i] = height of internal node i's subtree (a node over two triangles has height 1): read
 // for the subtrees hanging off the treelet, written for every node slot of the treelet, x included.
-PRT_HD bool treelet_optimise(Node *nodes, int32_t x, int32_t *depth) {
+PRT_HD bool treelet_optimise(Node *nodes, int32_t x, int32_t *depth, bool strict = false) {
 	Treelet t;
 	float area[TREELET_SETS], copt[TREELET_SETS];
 	uint8_t part[TREELET_SETS];
 	treelet_form(nodes, x, depth, t);
 	treelet_dp(t, area, copt, part);
-	return treelet_commit(nodes, t, area, copt, part, depth);
+	return treelet_commit(nodes, t, area, copt, part, depth, strict);
 }
 
 } // namespace prt

@@ -30,7 +30,7 @@ class Emu:
         L.emu_load.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int32]
         L.emu_free.argtypes = [C.c_void_p]
         L.emu_treelet.restype = C.c_int32
-        L.emu_treelet.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
+        L.emu_treelet.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
         L.emu_num_nodes.restype = C.c_uint64
         L.emu_num_nodes.argtypes = [C.c_void_p]
         L.emu_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -55,10 +55,10 @@ class Emu:
         self.h = self.L.emu_load(nodes.ctypes.data, nodes.nbytes // 64, tris.ctypes.data, self.n, root)
         return self
 
-    def treelet(self, passes=1):
+    def treelet(self, passes=1, strict=False):
         """opt-in SAH optimisation (prt_treelet.cuh) -> (tree height, treelets changed in last pass)"""
         ch = C.c_uint64(0)
-        d = self.L.emu_treelet(self.h, int(passes), C.byref(ch))
+        d = self.L.emu_treelet(self.h, int(passes), int(strict), C.byref(ch))
         return int(d), int(ch.value)
 
     def free(self):

@@ -89,14 +89,15 @@ Box refit(Emu &e, const std::vector<Box> &leaf, int32_t ref) {
 } // namespace
 
 // sequential stand-in for k_treelet (build.cu): children before parents, same per-node rule
-int32_t treelet_walk(Emu &e, int32_t x, std::vector<int32_t> &depth, int32_t &count, uint64_t &changed) {
+int32_t treelet_walk(Emu &e, int32_t x, std::vector<int32_t> &depth, int32_t &count, uint64_t &changed,
+                     bool strict) {
 	const int32_t c0 = e.nodes[x].child0, c1 = e.nodes[x].child1;
 	int32_t n0 = 1, n1 = 1;
-	const int32_t d0 = c0 < 0 ? 0 : treelet_walk(e, c0, depth, n0, changed);
-	const int32_t d1 = c1 < 0 ? 0 : treelet_walk(e, c1, depth, n1, changed);
+	const int32_t d0 = c0 < 0 ? 0 : treelet_walk(e, c0, depth, n0, changed, strict);
+	const int32_t d1 = c1 < 0 ? 0 : treelet_walk(e, c1, depth, n1, changed, strict);
 	count = n0 + n1;
 	if (count >= TREELET_N)
-		changed += treelet_optimise(e.nodes.data(), x, depth.data()) ? 1 : 0;
+		changed += treelet_optimise(e.nodes.data(), x, depth.data(), strict) ? 1 : 0;
 	else
 		depth[x] = 1 + std::max(d0, d1);
 	return depth[x];
@@ -106,7 +107,7 @@ extern "C" {
 
 // `passes` rounds of treelet restructuring; returns the height of the tree, *changed = treelets
 // whose topology was replaced in the last pass
-int32_t emu_treelet(void *h, int passes, uint64_t *changed) {
+int32_t emu_treelet(void *h, int passes, int strict, uint64_t *changed) {
 	Emu *e = static_cast<Emu *>(h);
 	if (e->n < (uint64_t)TREELET_N)
 		return 0;
@@ -115,7 +116,7 @@ int32_t emu_treelet(void *h, int passes, uint64_t *changed) {
 	for (int p = 0; p < passes; ++p) {
 		int32_t cnt = 0;
 		uint64_t ch = 0;
-		d = treelet_walk(*e, e->root, depth, cnt, ch);
+		d = treelet_walk(*e, e->root, depth, cnt, ch, strict != 0);
 		if (changed)
 			*changed = ch;
 	}
