@@ -134,9 +134,10 @@ int prt_b200_set_trace_opts(prt_b200 *ctx, const prt_trace_opts *opts);
  * the number of boxes visited per ray (measured: -6 % on C2, -46 % on the C3 interior).
  *   mode 0  never: set_tris leaves the radix tree as built (fastest build)
  *   mode 1  inside every set_tris
- *   mode 2  (default) lazily: once a scene has been asked for 16 rays per triangle -- about what the
- *           optimisation costs -- it is optimised before the next batch is traced; a scene rebuilt
- *           every frame (config C5) never pays for it, a static one pays once
+ *   mode 2  (default) lazily: once a scene has been asked for max(32 rays per triangle, 8 Mi rays)
+ *           -- about when tracing the plain tree has cost what the optimisation costs -- it is
+ *           optimised before the next batch is traced; a scene rebuilt every frame (config C5)
+ *           never pays for it, a static one pays once
  * passes: 1..8 (default 2).  Env PRT_B200_TREELET_MODE / PRT_B200_TREELET_PASSES.
  * prt_b200_tree_depth: height of the optimised tree (0 = the current tree is the plain radix tree);
  * prt_b200_last_optimise_ms: device time the lazy optimisation of the current scene took. */

@@ -161,7 +161,8 @@ class CUDABackend(Backend):
 
     def set_tree_optimisation(self, mode: int, passes: int = 2):
         """SAH optimisation of the LBVH by treelet restructuring (Karras & Aila 2013): mode 0 never,
-        1 inside every set_tris, 2 (default) lazily once a scene has served 16 rays per triangle."""
+        1 inside every set_tris, 2 (default) lazily once a scene has served max(32 rays per triangle,
+        8 Mi rays)."""
         self._need()
         self._check(lib().prt_b200_set_tree_optimisation(self._h, int(mode), int(passes)))
 

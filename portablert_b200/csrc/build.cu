@@ -468,8 +468,10 @@ __global__ void __launch_bounds__(256)
 // lanes each and the full set by all 32, merged with shuffles on the key (cost, half).
 struct TreeletShared {
 	Treelet t;
+	TreeletPlan plan;
 	float area[TREELET_SETS], copt[TREELET_SETS];
 	uint8_t part[TREELET_SETS];
+	int commit;
 };
 
 __device__ __forceinline__ void reduce_split(float &best, int &bp, int width) {
@@ -489,11 +491,16 @@ __device__ void treelet_optimise_warp(Node *nodes, int32_t x, int32_t *depth, Tr
 	if (lane == 0)
 		treelet_form(nodes, x, depth, sh.t);
 	__syncwarp();
-	for (int s = lane; s < TREELET_SETS; s += 32) {
-		sh.area[s] = s ? treelet_subset_area(sh.t, s) : 0.0f;
-		if ((s & (s - 1)) == 0) {
-			sh.copt[s] = 0.0f;
-			sh.part[s] = 0;
+	{ // subsets lane, lane+32, lane+64, lane+96 share their five low leaves
+		const Box low = treelet_subset_box(sh.t, lane, empty_box(), 0, 5);
+#pragma unroll
+		for (int hi = 0; hi < 4; ++hi) {
+			const int s = (int)lane | (hi << 5);
+			sh.area[s] = s ? box_half_area(treelet_subset_box(sh.t, s, low, 5, TREELET_N)) : 0.0f;
+			if ((s & (s - 1)) == 0) {
+				sh.copt[s] = 0.0f;
+				sh.part[s] = 0;
+			}
 		}
 	}
 	__syncwarp();
@@ -514,7 +521,7 @@ __device__ void treelet_optimise_warp(Node *nodes, int32_t x, int32_t *depth, Tr
 		float best = INFINITY;
 		int bp = 0xff;
 		if (s)
-			treelet_best_split(sh.copt, s, lane & 3, 4, best, bp);
+			treelet_best_split_quarter(sh.copt, s, lane & 3, best, bp);
 		reduce_split(best, bp, 4);
 		if (s && (lane & 3) == 0) {
 			sh.copt[s] = fadd(sh.area[s], best);
@@ -522,11 +529,21 @@ __device__ void treelet_optimise_warp(Node *nodes, int32_t x, int32_t *depth, Tr
 		}
 	}
 	__syncwarp();
-	{ // the full set: 63 splits over 32 lanes
+	{ // the full set: its 63 splits are p = 2, 4, .. 126 (leaf 0 stays in the other half)
 		const int s = TREELET_SETS - 1;
-		float best;
-		int bp;
-		treelet_best_split(sh.copt, s, lane, 32, best, bp);
+		float best = INFINITY;
+		int bp = 0xff;
+#pragma unroll
+		for (int i = 0; i < 2; ++i) {
+			const int p = ((int)lane + 32 * i + 1) << 1;
+			if (p < s) {
+				const float c = fadd(sh.copt[p], sh.copt[s ^ p]);
+				if (c < best) {
+					best = c;
+					bp = p;
+				}
+			}
+		}
 		reduce_split(best, bp, 32);
 		if (lane == 0) {
 			sh.copt[s] = fadd(sh.area[s], best);
@@ -534,9 +551,17 @@ __device__ void treelet_optimise_warp(Node *nodes, int32_t x, int32_t *depth, Tr
 		}
 	}
 	__syncwarp();
-	if (lane == 0) {
-		treelet_commit(nodes, sh.t, sh.area, sh.copt, sh.part, depth, strict);
-		__threadfence(); // the lane that owns x publishes it to its parent's other subtree next round
+	if (lane == 0)
+		sh.commit = treelet_plan(sh.t, sh.area, sh.copt, sh.part, depth, strict, sh.plan) ? 1 : 0;
+	__syncwarp();
+	if (sh.commit) { // the boxes and halves of the (up to) six nodes, one child per lane
+		const int k = lane >> 1, side = lane & 1;
+		if (k < sh.plan.used) {
+			treelet_write_side(nodes, sh.t, sh.plan, k, side);
+			if (side == 0)
+				depth[sh.t.slot[k]] = sh.plan.slot_depth[k];
+			__threadfence(); // the lane that owns x publishes it to its parent's other subtree next round
+		}
 	}
 	__syncwarp();
 }
@@ -742,14 +767,16 @@ int optimise_tree(prt_b200 *c, cudaStream_t s) {
 }
 
 // Lazy mode (the default): a scene that keeps being traced is optimised once it has been asked for
-// LAZY_RAYS_PER_TRI rays per triangle -- about what the optimisation costs in traversal time --
-// so a per-frame rebuild (config C5: 8 rays per triangle and frame) never pays for it while a
-// static scene gets the better tree from its first or second batch on.  Called by the trace entry
-// points (api.cu) before they launch anything.
+// max(LAZY_RAYS_PER_TRI rays per triangle, LAZY_MIN_RAYS) rays -- roughly when the time spent
+// tracing the plain tree equals what the optimisation costs (measured: 0.5 ms + 1.2 ms per million
+// triangles and pass against 0.15-0.4 ns per ray), the break-even rule that is never more than
+// twice as expensive as knowing the future.  A per-frame rebuild (config C5: 8 rays per triangle
+// and frame) never pays for it; a static scene gets the better tree after a few batches.  Called
+// by the trace entry points (api.cu) before they launch anything.
 int maybe_optimise_tree(prt_b200 *c, uint64_t n_rays) {
 	c->rays_since_build += n_rays;
 	if (c->optimise_mode != 2 || c->tree_optimised || c->n_tris < (uint64_t)TREELET_N ||
-	    c->rays_since_build < LAZY_RAYS_PER_TRI * c->n_tris)
+	    c->rays_since_build < std::max<uint64_t>(LAZY_RAYS_PER_TRI * c->n_tris, LAZY_MIN_RAYS))
 		return PRT_OK;
 	cudaStream_t s = c->stream;
 	PRT_CUDA(c, cudaEventRecord(c->ev0, s));

@@ -150,7 +150,8 @@ inline int fail(prt_b200 *c, int code, const char *what, cudaError_t e = cudaSuc
 
 // build.cu
 constexpr int MAX_TREE_DEPTH = 96;          // what prt_traverse.cuh: STACK_DEPTH is sized for
-constexpr uint64_t LAZY_RAYS_PER_TRI = 16;  // lazy tree optimisation threshold
+constexpr uint64_t LAZY_RAYS_PER_TRI = 32;  // lazy tree optimisation threshold: max(32 rays per
+constexpr uint64_t LAZY_MIN_RAYS = 8u << 20; // triangle, 8 Mi rays) since the last set_tris
 int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n);
 int optimise_tree(prt_b200 *c, cudaStream_t s);
 int maybe_optimise_tree(prt_b200 *c, uint64_t n_rays);

@@ -131,15 +131,32 @@ PRT_HD void treelet_form(const Node *nodes, int32_t x, const int32_t *depth, Tre
 	t.old_cost = old_cost;
 }
 
-PRT_HD float treelet_subset_area(const Treelet &t, int s) {
-	Box b;
-	bool first = true;
-	for (int k = 0; k < t.n; ++k)
-		if (s & (1 << k)) {
-			b = first ? t.leaf_box[k] : box_union(b, t.leaf_box[k]);
-			first = false;
+// Box of the union of the leaves in subset s, branch-free (the lanes of a warp evaluate different
+// subsets in lockstep): starting from the empty box, min/max with +-inf leave a box unchanged.
+PRT_HD Box treelet_subset_box(const Treelet &t, int s, Box b, int k0, int k1) {
+	for (int k = k0; k < k1; ++k) {
+		const bool take = (s >> k) & 1;
+#pragma unroll
+		for (int a = 0; a < 3; ++a) {
+			b.lo[a] = smin(b.lo[a], take ? t.leaf_box[k].lo[a] : INFINITY);
+			b.hi[a] = smax(b.hi[a], take ? t.leaf_box[k].hi[a] : -INFINITY);
 		}
-	return box_half_area(b);
+	}
+	return b;
+}
+
+PRT_HD Box empty_box() {
+	Box b;
+#pragma unroll
+	for (int a = 0; a < 3; ++a) {
+		b.lo[a] = INFINITY;
+		b.hi[a] = -INFINITY;
+	}
+	return b;
+}
+
+PRT_HD float treelet_subset_area(const Treelet &t, int s) {
+	return box_half_area(treelet_subset_box(t, s, empty_box(), 0, t.n));
 }
 
 // Best split of subset s (>= 2 leaves) into two non-empty halves, given copt of all its proper
@@ -163,6 +180,29 @@ PRT_HD void treelet_best_split(const float *copt, int s, int sub, int nsub, floa
 		++i;
 		p = (p - delta) & s;
 	} while (p != 0);
+}
+
+// The same search restricted to the splits whose two lowest candidate bits equal `sub` (0..3): four
+// lanes cover a subset without diverging; each runs through its candidates in increasing order.
+PRT_HD void treelet_best_split_quarter(const float *copt, int s, int sub, float &best, int &bp) {
+	const int delta = (s - 1) & s;
+	const int b0 = delta & -delta, r0 = delta ^ b0;
+	const int b1 = r0 & -r0, rest = r0 ^ b1;
+	const int base = ((sub & 1) ? b0 : 0) | ((sub & 2) ? b1 : 0);
+	best = INFINITY;
+	bp = 0xff;
+	int q = 0;
+	do {
+		const int p = base | q;
+		if (p != 0) {
+			const float c = fadd(copt[p], copt[s ^ p]);
+			if (c < best) {
+				best = c;
+				bp = p;
+			}
+		}
+		q = (q - rest) & rest;
+	} while (q != 0);
 }
 
 PRT_HD int treelet_first_split(int s) {
@@ -190,18 +230,26 @@ PRT_HD void treelet_dp(const Treelet &t, float *area, float *copt, uint8_t *part
 	}
 }
 
-// Replace the treelet's topology by the optimal one if that lowers the summed area.  Sets depth[]
-// of every node slot written (or of the root alone when the topology stays).  Returns true when
-// the topology was replaced.
+// The optimal topology laid out over the treelet's node slots (parents before children: slot k's
+// children take the next free slots).
+struct TreeletPlan {
+	int used;                          // node slots written
+	uint8_t half[TREELET_N - 1][2];    // leaf subset below each child
+	int32_t ref[TREELET_N - 1][2];     // child reference to store
+	int32_t slot_depth[TREELET_N - 1]; // height of the subtree of each slot
+};
+
+// Decide whether the treelet's topology is replaced by the optimal one (only if that lowers the
+// summed area) and lay the new topology out.  Sets depth[] of the root when the topology stays.
 // `strict`: additionally refuse a topology that makes the subtree of x taller than it is.  By
 // induction over the bottom-up order every subtree then stays at most as tall as in the radix tree,
 // whose height is bounded by the key length -- the bound the traversal stack is sized for
 // (prt_traverse.cuh: STACK_DEPTH).  It costs quality (big triangles want to sit high up, in a
 // locally deeper tree), so the build first runs without it, measures the height of the result and
 // only falls back to the strict rule if that exceeds the bound (build.cu: optimise_tree).
-PRT_HD bool treelet_commit(Node *nodes, const Treelet &t, const float *area, const float *copt,
-                           const uint8_t *part, int32_t *depth, bool strict) {
-	const int n = t.n, full = (1 << n) - 1;
+PRT_HD bool treelet_plan(const Treelet &t, const float *area, const float *copt, const uint8_t *part,
+                         int32_t *depth, bool strict, TreeletPlan &pl) {
+	const int full = (1 << t.n) - 1;
 	const int32_t x = t.slot[0];
 	const int32_t c0 = t.root_child[0], c1 = t.root_child[1];
 	const int32_t d0 = c0 < 0 ? 0 : treelet_load_i32(depth + c0);
@@ -210,54 +258,62 @@ PRT_HD bool treelet_commit(Node *nodes, const Treelet &t, const float *area, con
 	depth[x] = old_depth;
 	if (!(copt[full] < fadd(t.old_cost, area[full])))
 		return false;
-	// parents before children: slot k's children take the next free slots
-	uint8_t todo_set[TREELET_N - 1];
 	int8_t kid[TREELET_N - 1][2]; // >= 0: slot number, < 0: ~leaf number
-	todo_set[0] = (uint8_t)full;
+	pl.half[0][0] = part[full];
+	pl.half[0][1] = (uint8_t)(full ^ part[full]);
 	int used = 1;
 	for (int k = 0; k < used; ++k) {
-		const int s = todo_set[k];
-		const int half[2] = {part[s], s ^ part[s]};
 		for (int side = 0; side < 2; ++side) {
-			const int h = half[side];
+			const int h = pl.half[k][side];
 			if ((h & (h - 1)) == 0) {
 				int only = 0;
 				while (!(h & (1 << only)))
 					++only;
 				kid[k][side] = (int8_t)~only;
+				pl.ref[k][side] = t.leaf_ref[only];
 			} else {
-				todo_set[used] = (uint8_t)h;
+				pl.half[used][0] = part[h];
+				pl.half[used][1] = (uint8_t)(h ^ part[h]);
 				kid[k][side] = (int8_t)used;
+				pl.ref[k][side] = t.slot[used];
 				++used;
 			}
 		}
 	}
-	int32_t slot_depth[TREELET_N - 1];
 	for (int k = used - 1; k >= 0; --k) {
 		int32_t d[2];
 		for (int side = 0; side < 2; ++side)
-			d[side] = kid[k][side] < 0 ? t.leaf_depth[~kid[k][side]] : slot_depth[kid[k][side]];
-		slot_depth[k] = 1 + (d[0] > d[1] ? d[0] : d[1]);
+			d[side] = kid[k][side] < 0 ? t.leaf_depth[~kid[k][side]] : pl.slot_depth[kid[k][side]];
+		pl.slot_depth[k] = 1 + (d[0] > d[1] ? d[0] : d[1]);
 	}
-	if (strict && slot_depth[0] > old_depth)
+	pl.used = used;
+	return !(strict && pl.slot_depth[0] > old_depth);
+}
+
+// One child (box + reference) of node slot k of the new topology; side 0 also clears the padding.
+PRT_HD void treelet_write_side(Node *nodes, const Treelet &t, const TreeletPlan &pl, int k, int side) {
+	const Box b = treelet_subset_box(t, pl.half[k][side], empty_box(), 0, t.n);
+	float *f = reinterpret_cast<float *>(nodes + t.slot[k]);
+	int32_t *w = reinterpret_cast<int32_t *>(nodes + t.slot[k]);
+#pragma unroll
+	for (int a = 0; a < 3; ++a) {
+		f[6 * side + a] = b.lo[a];
+		f[6 * side + 3 + a] = b.hi[a];
+	}
+	w[12 + side] = pl.ref[k][side];
+	if (side == 0)
+		w[14] = w[15] = 0;
+}
+
+PRT_HD bool treelet_commit(Node *nodes, const Treelet &t, const float *area, const float *copt,
+                           const uint8_t *part, int32_t *depth, bool strict) {
+	TreeletPlan pl;
+	if (!treelet_plan(t, area, copt, part, depth, strict, pl))
 		return false;
-	for (int k = 0; k < used; ++k) {
-		const int s = todo_set[k];
-		const int half[2] = {part[s], s ^ part[s]};
-		Node nd;
-		nd.pad0 = nd.pad1 = 0;
-		for (int side = 0; side < 2; ++side) {
-			Box b;
-			bool first = true;
-			for (int j = 0; j < n; ++j)
-				if (half[side] & (1 << j)) {
-					b = first ? t.leaf_box[j] : box_union(b, t.leaf_box[j]);
-					first = false;
-				}
-			set_child(nd, side, kid[k][side] < 0 ? t.leaf_ref[~kid[k][side]] : t.slot[kid[k][side]], b);
-		}
-		treelet_store(nodes, t.slot[k], nd);
-		depth[t.slot[k]] = slot_depth[k];
+	for (int k = 0; k < pl.used; ++k) {
+		treelet_write_side(nodes, t, pl, k, 0);
+		treelet_write_side(nodes, t, pl, k, 1);
+		depth[t.slot[k]] = pl.slot_depth[k];
 	}
 	return true;
 }
