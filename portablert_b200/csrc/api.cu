@@ -151,6 +151,13 @@ int prt_b200_create(prt_b200 **out, int device) {
 		c->wide_mode = std::max(0, std::min(2, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_SORT_RAYS"))
 		c->sort_rays = std::max(0, std::min(2, std::atoi(e)));
+	if (const char *e = std::getenv("PRT_B200_RAYKEY")) {
+		int ob = 0, db = 0;
+		if (std::sscanf(e, "%d,%d", &ob, &db) == 2 && ob >= 1 && ob <= 10 && db >= 0 && db <= 10) {
+			c->ray_key_ob = ob;
+			c->ray_key_db = db;
+		}
+	}
 	if (const char *e = std::getenv("PRT_B200_PIPE_TRACE"))
 		c->pipe_trace = std::atoi(e) != 0;
 	if (const char *e = std::getenv("PRT_B200_CHUNK_LOG2"))

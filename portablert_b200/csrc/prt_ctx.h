@@ -108,6 +108,7 @@ struct prt_b200 {
 	prt::DevBuf probe_ticket;                    // 2 x u64 block tickets of the coherence probe
 	unsigned long long *probe_host = nullptr;    // 2 x u64 mapped pinned flags (host view)
 	unsigned long long *probe_dev = nullptr;     // ... and their device view
+	int ray_key_ob = 4, ray_key_db = 4; // sort key bits per axis: origin, direction (env PRT_B200_RAYKEY="ob,db")
 	int sort_rays = 2; // env PRT_B200_SORT_RAYS: 0 never, 1 always, 2 auto (only incoherent batches)
 	float scene_lo[3] = {0.f, 0.f, 0.f}, scene_hi[3] = {0.f, 0.f, 0.f};
 	uint64_t sorted_batches = 0, unsorted_batches = 0, wide_batches = 0;

@@ -60,12 +60,26 @@ __device__ __forceinline__ uint32_t ray_key(const float *__restrict__ r, float3 
 	                  lo, inv_ext);
 }
 
+// Sort key with `ob` bits per axis of the origin above `db` bits per axis of the direction (the
+// probe's fixed 4 + 4 key only decides WHETHER to sort).
 __global__ void __launch_bounds__(256)
-    k_ray_keys(const float *__restrict__ rays, uint64_t n, float3 lo, float3 inv_ext,
+    k_ray_keys(const float *__restrict__ rays, uint64_t n, float3 lo, float3 inv_ext, int ob, int db,
                uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) {
-		keys[i] = ray_key(rays + i * 6, lo, inv_ext);
+		const float *r = rays + i * 6;
+		const float ox = __ldg(r), oy = __ldg(r + 1), oz = __ldg(r + 2);
+		const float dx = __ldg(r + 3), dy = __ldg(r + 4), dz = __ldg(r + 5);
+		const float inv = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-37f));
+		const float no = (float)(1 << ob), nd = (float)(1 << db);
+		// NaN / out-of-box values clamp into the grid; the key only steers the processing order
+		const uint32_t qx = (uint32_t)fminf(fmaxf((ox - lo.x) * inv_ext.x * no, 0.f), no - 1.f);
+		const uint32_t qy = (uint32_t)fminf(fmaxf((oy - lo.y) * inv_ext.y * no, 0.f), no - 1.f);
+		const uint32_t qz = (uint32_t)fminf(fmaxf((oz - lo.z) * inv_ext.z * no, 0.f), no - 1.f);
+		const uint32_t ux = (uint32_t)fminf(fmaxf((dx * inv * 0.5f + 0.5f) * nd, 0.f), nd - 1.f);
+		const uint32_t uy = (uint32_t)fminf(fmaxf((dy * inv * 0.5f + 0.5f) * nd, 0.f), nd - 1.f);
+		const uint32_t uz = (uint32_t)fminf(fmaxf((dz * inv * 0.5f + 0.5f) * nd, 0.f), nd - 1.f);
+		keys[i] = (morton3(qx, qy, qz) << (3 * db)) | morton3(ux, uy, uz);
 		vals[i] = (uint32_t)i;
 	}
 }
@@ -107,7 +121,6 @@ static void k_ray_probe_launch(prt_b200 *c, const float *rays, uint64_t n, float
 	c->launches += 1;
 }
 
-constexpr int RAY_KEY_BITS = 24;
 constexpr uint64_t SORT_MIN_RAYS = 1u << 16;
 
 
@@ -228,14 +241,15 @@ int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, c
 		}
 		if (do_sort) {
 			k_ray_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
-			    d_rays6, n, lo, ie, rs.keys[0].as<uint64_t>(), rs.vals[0].as<uint32_t>());
+			    d_rays6, n, lo, ie, c->ray_key_ob, c->ray_key_db, rs.keys[0].as<uint64_t>(),
+			    rs.vals[0].as<uint32_t>());
 			c->launches += 1;
 		}
 		if (do_sort) {
 			uint64_t *const kk[2] = {rs.keys[0].as<uint64_t>(), rs.keys[1].as<uint64_t>()};
 			uint32_t *const vv[2] = {rs.vals[0].as<uint32_t>(), rs.vals[1].as<uint32_t>()};
 			int cur = 0;
-			if (int rc = radix_sort_pairs(c, rs.scratch, kk, vv, n, RAY_KEY_BITS, s, &cur))
+			if (int rc = radix_sort_pairs(c, rs.scratch, kk, vv, n, 3 * (c->ray_key_ob + c->ray_key_db), s, &cur))
 				return rc;
 			P.perm = vv[cur];
 			c->sorted_batches++;

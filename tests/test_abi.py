@@ -67,3 +67,16 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert "liboracle" not in txt and "libprt_ref" not in txt and "libprt_emu" not in txt, f
+
+
+def test_cmake_build_lists_the_same_sources_as_the_makefile():
+    """CMakeLists.txt (for CMake checkouts like the reference) must not drift from the in-tree
+    Makefile the tests and the bench use."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mk = open(os.path.join(root, "portablert_b200", "csrc", "Makefile")).read()
+    cm = open(os.path.join(root, "CMakeLists.txt")).read()
+    mk_src = set(re.findall(r"\$\(HERE\)(\w+\.cu)", mk))
+    cm_src = set(re.findall(r"\$\{SRC\}/(\w+\.cu)", cm))
+    assert mk_src == cm_src and "100a" in cm and "USE_CUDA" in open(
+        os.path.join(root, "cmake", "portableRT_use_cuda.cmake")).read()
