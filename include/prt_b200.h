@@ -140,10 +140,14 @@ int prt_b200_set_trace_opts(prt_b200 *ctx, const prt_trace_opts *opts);
  *           never pays for it, a static one pays once
  * passes: 1..8 (default 2).  Env PRT_B200_TREELET_MODE / PRT_B200_TREELET_PASSES.
  * prt_b200_tree_depth: height of the optimised tree (0 = the current tree is the plain radix tree);
- * prt_b200_last_optimise_ms: device time the lazy optimisation of the current scene took. */
+ * prt_b200_last_optimise_ms: device time the lazy optimisation of the current scene took.
+ * The traversal stack is sized for the radix tree's height bound (96); an optimised tree that comes
+ * out taller is discarded and the optimisation repeated under a height-preserving rule
+ * (prt_b200_strict_fallbacks counts these; none on any benchmark scene). */
 int prt_b200_set_tree_optimisation(prt_b200 *ctx, int mode, int passes);
 int32_t prt_b200_tree_depth(const prt_b200 *ctx);
 float prt_b200_last_optimise_ms(const prt_b200 *ctx);
+uint64_t prt_b200_strict_fallbacks(const prt_b200 *ctx);
 
 /* Triangle test: 0 (default) = the reference's Moeller-Trumbore arithmetic replayed operation for
  * operation (core.hpp:27-65) -- results identical to the reference CPU backend; 1 = opt-in

@@ -173,6 +173,11 @@ class CUDABackend(Backend):
         return int(lib().prt_b200_tree_depth(self._h))
 
     @property
+    def strict_fallbacks(self) -> int:
+        self._need()
+        return int(lib().prt_b200_strict_fallbacks(self._h))
+
+    @property
     def last_optimise_ms(self) -> float:
         self._need()
         return float(lib().prt_b200_last_optimise_ms(self._h))

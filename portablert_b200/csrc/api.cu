@@ -143,6 +143,8 @@ int prt_b200_create(prt_b200 **out, int device) {
 		c->fast_boxes = std::atoi(e) != 0;
 	if (const char *e = std::getenv("PRT_B200_TREELET_MODE"))
 		c->optimise_mode = std::max(0, std::min(2, std::atoi(e)));
+	if (const char *e = std::getenv("PRT_B200_MAX_TREE_DEPTH")) // tests: force the strict fallback
+		c->max_tree_depth = std::max(1, std::min(96, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_TREELET_PASSES"))
 		c->optimise_passes = std::max(1, std::min(8, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_WATERTIGHT"))
@@ -237,6 +239,7 @@ int prt_b200_set_tree_optimisation(prt_b200 *c, int mode, int passes) {
 }
 int32_t prt_b200_tree_depth(const prt_b200 *c) { return c ? c->tree_depth : 0; }
 float prt_b200_last_optimise_ms(const prt_b200 *c) { return c ? c->last_optimise_ms : 0.f; }
+uint64_t prt_b200_strict_fallbacks(const prt_b200 *c) { return c ? c->strict_fallbacks : 0; }
 
 int prt_b200_set_triangle_test(prt_b200 *c, int mode) {
 	if (!c || mode < 0 || mode > 1)

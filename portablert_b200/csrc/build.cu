@@ -752,7 +752,7 @@ int optimise_tree(prt_b200 *c, cudaStream_t s) {
 		return rc;
 	PRT_CUDA(c, cudaMemcpyAsync(&depth, depth_src, 4, cudaMemcpyDeviceToHost, s));
 	PRT_CUDA(c, cudaStreamSynchronize(s));
-	if (depth > MAX_TREE_DEPTH) {
+	if (depth > c->max_tree_depth) {
 		PRT_CUDA(c, cudaMemcpyAsync(c->nodes.p, c->tl_backup.p, (n - 1) * sizeof(Node),
 		                            cudaMemcpyDeviceToDevice, s));
 		if (int rc = treelet_passes(c, s, c->optimise_passes, true))

@@ -95,6 +95,7 @@ struct prt_b200 {
 	int optimise_passes = 2; // env PRT_B200_TREELET_PASSES
 	bool tree_optimised = false;
 	uint64_t rays_since_build = 0, strict_fallbacks = 0;
+	int max_tree_depth = 96; // what prt_traverse.cuh: STACK_DEPTH is sized for (env PRT_B200_MAX_TREE_DEPTH: tests)
 	float last_optimise_ms = 0.f; // device time of the lazy optimisation of the current scene (0 = none yet)
 	int32_t tree_depth = 0;       // height of the optimised tree (0 = not optimised)
 	int32_t root = 0; // index of the root node (the radix tree numbers nodes by split position)
@@ -150,7 +151,6 @@ inline int fail(prt_b200 *c, int code, const char *what, cudaError_t e = cudaSuc
 	} while (0)
 
 // build.cu
-constexpr int MAX_TREE_DEPTH = 96;          // what prt_traverse.cuh: STACK_DEPTH is sized for
 constexpr uint64_t LAZY_RAYS_PER_TRI = 32;  // lazy tree optimisation threshold: max(32 rays per
 constexpr uint64_t LAZY_MIN_RAYS = 8u << 20; // triangle, 8 Mi rays) since the last set_tris
 int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n);

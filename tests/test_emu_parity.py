@@ -305,3 +305,29 @@ def test_treelet_optimisation_keeps_results_and_lowers_sah_cost(name, emu):
           "tris/ray", before["counts"][:, 1].mean(), "->", after["counts"][:, 1].mean())
     if name == "interior":
         assert after["counts"].sum() < before["counts"].sum()
+
+
+def test_treelet_strict_rule_never_makes_the_tree_taller(emu):
+    """the fallback rule of treelet_plan (strict): heights only shrink, results unchanged, and the
+    cost still drops -- less than without the rule, which is why it is only a fallback"""
+    from bvhcheck import sah_internal_area
+    tris, rays = CASES["interior"]
+    emu.build(tris, 10)
+    before = emu.trace(rays)
+    nodes, recs = emu.download()
+    h0, c0 = check_bvh(nodes, recs, tris), sah_internal_area(nodes)
+    heights = []
+    for _ in range(3):
+        d, _ = emu.treelet(1, strict=True)
+        nodes, recs = emu.download()
+        assert check_bvh(nodes, recs, tris) == d
+        heights.append(d)
+    assert all(h <= h0 for h in heights), (h0, heights)
+    c_strict = sah_internal_area(nodes)
+    after = emu.trace(rays)
+    for k in ("valid", "t", "pid", "u", "v"):
+        assert np.array_equal(after[k], before[k], equal_nan=True), k
+    emu.build(tris, 10)
+    emu.treelet(3)
+    c_free = sah_internal_area(emu.download()[0])
+    assert c_free < c_strict < c0, (c_free, c_strict, c0)

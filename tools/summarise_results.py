@@ -23,9 +23,13 @@ def main():
            "stream the kernels run on, L2 flushed (256 MiB memset) between timed steps, mean of the "
            "timed steps.  e2e: host buffers in, host `HitReg` records out through "
            "`prt_b200_nearest_hits` (pinned host memory, H2D + kernels + D2H inside the timed region).\n",
+           "Static scenes (C2, C3, C3B, C4) are traced on the tree the default lazy mode leaves after "
+           "max(32 rays per triangle, 8 Mi rays): the LBVH optimised by 2 treelet passes; C5 rebuilds "
+           "the plain LBVH before every step (dynamic scene).  `build ms` = set_tris as called "
+           "(plain LBVH); `build+opt ms` = the same with the optimisation inside set_tris.\n",
            "| config | tris | rays | tags | trace ms | Mrays/s | nodes/ray | tris/ray | B/ray | "
-           "fetched GB/s | of L2 read peak | build ms | Mtris/s | e2e Mrays/s |",
-           "|---|---:|---:|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|"]
+           "fetched GB/s | of L2 read peak | build ms | Mtris/s | build+opt ms | Mtris/s | tree height | e2e Mrays/s |",
+           "|---|---:|---:|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|"]
     for cfg in ("c2", "c3", "c3b", "c5", "c4"):
         d = load(f"bench_{cfg}.json")
         if not d:
@@ -35,7 +39,9 @@ def main():
                    f"mask {d['config']['tag_mask']} | {d['ms_per_step']:.3f} | {d['value']:.0f} | "
                    f"{r['nodes_per_ray']:.1f} | {r['tris_per_ray']:.2f} | {r['bytes_per_ray']:.0f} | "
                    f"{r['achieved']:.0f} | {r['frac_of_l2']:.2f} | {d['build']['ms']:.3f} | "
-                   f"{d['build']['mtris_s']:.0f} | {d['e2e']['value']:.0f} |")
+                   f"{d['build']['mtris_s']:.0f} | {d['build']['ms_with_optimisation']:.3f} | "
+                   f"{d['build']['mtris_s_with_optimisation']:.0f} | {d['build']['tree_height'] or '-'} | "
+                   f"{d['e2e']['value']:.0f} |")
     d = load("bench_c2.json")
     if d:
         r = d["roofline"]
@@ -55,6 +61,17 @@ def main():
         if pm:
             out.append("C2, all 31 tag combinations (device-timed Mrays/s): " +
                        ", ".join(f"{k} {v:.0f}" for k, v in pm.items()) + "\n")
+    out.append("Opt-in watertight triangle test beside the default (same rays, same tree state): "
+               "Mrays/s, rays whose `valid` differs, rays whose t differs by more than 1e-5 relative:\n")
+    out.append("| config | default Mrays/s | watertight Mrays/s | valid differs | t differs > 1e-5 rel |")
+    out.append("|---|---:|---:|---:|---:|")
+    for cfg in ("c2", "c3", "c3b", "c5", "c4"):
+        d = load(f"bench_{cfg}.json")
+        if d and d.get("watertight"):
+            w = d["watertight"]
+            out.append(f"| {cfg.upper()} | {d['value']:.0f} | {w['value']:.0f} | {w['valid_differs']} | "
+                       f"{w['t_rel_gt_1e-5']} |")
+    out.append("")
     ref = load("bench_c2_ref.json")
     if ref:
         out.append(f"`bench.py --impl reference` (same box): {ref['value']:.1f} Mrays/s, "
@@ -65,7 +82,10 @@ def main():
         if d:
             rows.append(f"| {n} | {d['value']:.0f} | {d['ms_per_step']:.3f} | {d['e2e']['value']:.0f} | "
                         f"{d['e2e']['ms_per_step']:.2f} |")
-    if rows:
+    prev = os.path.join(ROOT, "profiles", "r01_results_earlier.md")
+    if os.path.exists(prev):
+        out.append(open(prev).read())
+    if len(rows) > 1:
         out.append("## Multi-GPU (C2, weak scaling: N frames of 2 073 600 rays, one rank per GPU, torchrun)\n")
         out.append("| GPUs | device-timed Mrays/s (whole job) | ms/step (max over ranks) | e2e Mrays/s | e2e ms/step |")
         out.append("|---:|---:|---:|---:|---:|")
