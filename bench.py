@@ -455,6 +455,31 @@ def main():
         te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te.item())
+        # What the platform allows: every rank moves exactly its slice's bytes host->device and
+        # device->host at the same time (two streams, no kernel), all ranks concurrently; the e2e
+        # call cannot beat this.  On a virtualised 8-GPU box the PCIe/IOMMU path is shared, so this
+        # floor -- not the GPUs -- decides how e2e scales with N.
+        import ctypes as C
+        cudart = C.CDLL("libcudart.so.12")
+        raw_in = np.ascontiguousarray(shm.my_rays).view(np.uint8).reshape(-1) \
+            if not shm.my_rays.flags["C_CONTIGUOUS"] else shm.my_rays.view(np.uint8).reshape(-1)
+        raw_out = shm.my_hits.view(np.uint8).reshape(-1)
+        d_in = torch.empty(raw_in.size, dtype=torch.uint8, device=dev)
+        d_out = torch.empty(raw_out.size, dtype=torch.uint8, device=dev)
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        floor_s = float("inf")
+        for _ in range(4):
+            barrier()
+            t0 = time.perf_counter()
+            cudart.cudaMemcpyAsync(C.c_void_p(d_in.data_ptr()), C.c_void_p(raw_in.ctypes.data),
+                                   C.c_size_t(raw_in.size), C.c_int(1), C.c_void_p(s_in.cuda_stream))
+            cudart.cudaMemcpyAsync(C.c_void_p(raw_out.ctypes.data), C.c_void_p(d_out.data_ptr()),
+                                   C.c_size_t(raw_out.size), C.c_int(2), C.c_void_p(s_out.cuda_stream))
+            barrier()
+            floor_s = min(floor_s, time.perf_counter() - t0)
+        tf = torch.tensor([floor_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        pcie_concurrent_floor_ms = float(tf.item()) * 1e3
         if rank == 0:  # the gathered result really is the whole batch, in ray order
             e2e_valid_fraction = float(np.asarray(shm.hits["valid"]).mean()) if mask & 16 else None
         barrier()
@@ -464,6 +489,11 @@ def main():
     e2e = {"value": total_rays / e2e_s / 1e6, "unit": "Mrays/s",
            "h2d_bytes_per_step": 24 * total_rays, "d2h_bytes_per_step": stride * total_rays,
            "ms_per_step": e2e_s * 1e3, "api": api}
+    if world > 1:
+        e2e["pcie_concurrent_floor_ms"] = pcie_concurrent_floor_ms
+        e2e["frac_of_pcie_floor"] = pcie_concurrent_floor_ms / (e2e_s * 1e3)
+        e2e["pcie_note"] = ("floor = all ranks copying their slices H2D and D2H concurrently, no kernels "
+                            "(best of 4, max over ranks, wall clock incl. one barrier)")
     if world == 1:
         e2e["pcie"] = pcie
         e2e["frac_of_pcie_floor"] = pcie["floor_ms"] / (e2e_s * 1e3)
