@@ -23,6 +23,22 @@ for tris in (scenes.KAT_TRI, scenes.blob(24, 24), scenes.interior(4000), np.repe
     parity.assert_parity(rep)
     for tags in (("valid",), ("t", "primitive_id"), ("uv", "p")):
         b.nearest_hits(rays[:5000], *tags)
+    # tree optimisation inside set_tris (k_parents, k_treelet; 3 passes) and wide nodes: same hits
+    b.set_tree_optimisation(1, 3)
+    b.set_wide_nodes(1)
+    b.set_tris(tris)
+    h2 = b.nearest_hits(rays)
+    for f in h.dtype.names:
+        assert np.array_equal(h[f], h2[f], equal_nan=True), f
+    # opt-in watertight kernels on the optimised tree
+    b.set_triangle_test(1)
+    b.set_tris(tris)
+    w = b.nearest_hits(rays)
+    assert (w["valid"] != h["valid"]).sum() <= 2
+    b.nearest_hits(rays[:5000], "valid")
+    b.set_triangle_test(0)
+    b.set_wide_nodes(2)
+    b.set_tree_optimisation(2, 2)
 print("sanitizer workload ok")
 PY
 for tool in memcheck racecheck synccheck; do
