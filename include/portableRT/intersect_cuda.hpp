@@ -94,6 +94,22 @@ class CUDABackend : public InvokableBackend<CUDABackend> {
 
 	prt_b200 *context() { return m_ctx; } // for benchmarks that use the device-resident entry points
 
+	// Extensions beyond the reference's Backend interface (reached through the concrete type, like
+	// the member form of nearest_hits); the same knobs exist as PRT_B200_* environment variables.
+	// SAH optimisation of the BVH by treelet restructuring: 0 never, 1 inside every set_tris,
+	// 2 (default) lazily for scenes that keep being traced.  Never changes a result.
+	void set_tree_optimisation(int mode, int passes = 2) {
+		need_ctx();
+		check(prt_b200_set_tree_optimisation(m_ctx, mode, passes));
+	}
+	// false (default): the reference's intersect_tri arithmetic (core.hpp:27-65), results identical
+	// to the CPU backend; true: watertight test (rays cannot slip between triangles sharing an edge
+	// or vertex), results differ from the reference on exactly those rays.  From the next set_tris.
+	void set_watertight(bool on) {
+		need_ctx();
+		check(prt_b200_set_triangle_test(m_ctx, on ? 1 : 0));
+	}
+
   private:
 #if defined(__GNUC__)
 #pragma GCC diagnostic push

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PRT_B200_ABI_VERSION 1
+#define PRT_B200_ABI_VERSION 2 /* 2: tree optimisation, triangle test */
 
 enum {
 	PRT_OK = 0,
@@ -189,7 +189,7 @@ uint64_t prt_b200_launch_count(const prt_b200 *ctx);   /* kernels launched by th
 float prt_b200_last_build_ms(const prt_b200 *ctx);     /* device time of the last build */
 float prt_b200_last_trace_ms(const prt_b200 *ctx);     /* device time of the last traversal */
 /* Copies the built BVH back to the host for structural tests: nodes (64 B each), triangle records
- * (48 B each).  Either pointer may be NULL. */
+ * (64 B each).  Either pointer may be NULL. */
 int prt_b200_download_bvh(const prt_b200 *ctx, void *nodes_out, void *tris_out);
 
 /* Roofline denominators measured on the box: read bandwidth (GB/s) of `bytes` of device memory

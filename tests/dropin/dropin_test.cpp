@@ -195,6 +195,28 @@ int main() {
 		neg += h.valid && h.t < 0;
 	CHECK(neg > 100, "the ray set must exercise negative-t hits (got %zu)", neg);
 
+	// extensions of the concrete type: SAH-optimised tree (results must not move) and the opt-in
+	// watertight test (may differ from the reference on edge-grazing rays only)
+	cb->set_tree_optimisation(1, 3);
+	cuda->set_tris(tris);
+	compare<ALL_TAGS>("full, tree optimised inside set_tris", nearest_hits(rays), ref, st);
+	cb->set_watertight(true);
+	cuda->set_tris(tris);
+	{
+		auto w = cb->nearest_hits<filter::valid, filter::t>(rays);
+		size_t differs = 0;
+		for (size_t i = 0; i < w.size(); ++i)
+			differs += w[i].valid != ref[i].valid;
+		CHECK(differs * 1000 < rays.size(), "watertight mode: %zu of %zu rays change validity", differs,
+		      rays.size());
+		std::printf("watertight mode: valid differs from the reference on %zu of %zu rays\n", differs,
+		            rays.size());
+	}
+	cb->set_watertight(false);
+	cb->set_tree_optimisation(2);
+	cuda->set_tris(tris);
+	compare<ALL_TAGS>("full, defaults restored", nearest_hits(rays), ref, st);
+
 	// empty scene and empty ray list (bvh.hpp:136-137)
 	cuda->set_tris({});
 	auto e = nearest_hits<filter::valid, filter::t>(rays);
