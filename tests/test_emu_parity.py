@@ -331,3 +331,26 @@ def test_treelet_strict_rule_never_makes_the_tree_taller(emu):
     emu.treelet(3)
     c_free = sah_internal_area(emu.download()[0])
     assert c_free < c_strict < c0, (c_free, c_strict, c0)
+
+
+def test_treelet_optimisation_survives_degenerate_triangles(emu):
+    """zero-area, duplicated, huge, NaN and infinite triangles: the optimiser neither crashes nor
+    changes a result (a NaN or infinite cost never wins a comparison, so such treelets stay put)"""
+    tris = scenes.blob(20, 20).copy()
+    tris[5] = tris[5][[0, 1, 2, 0, 1, 2, 0, 1, 2]]
+    tris[7:12] = tris[6]
+    tris[20] *= 1e30
+    tris[30, 4] = np.nan
+    tris[40, 2] = np.inf
+    tris[41, 0] = -np.inf
+    rays = scenes.pinhole_rays(64, 48)
+    emu.build(tris, 10)
+    before = emu.trace(rays)
+    depth, changed = emu.treelet(3)
+    assert changed > 0 and 0 < depth <= 96
+    for strict in (False, True):
+        emu.treelet(1, strict=strict)
+        after = emu.trace(rays)
+        for k in ("valid", "t", "pid", "u", "v"):
+            assert np.array_equal(after[k], before[k], equal_nan=True), k
+    assert np.array_equal(emu.trace(rays, wide=True)["t"], before["t"], equal_nan=True)
