@@ -607,6 +607,39 @@ def main():
                                       int(os.environ.get("PRT_B200_TREELET_PASSES", "2")))
         backend.set_tris_dev(d_tris.data_ptr(), n_tris)
 
+    # ---- C5 with temporal reuse (opt-in mode 3): distinct frames of the deforming height field; after
+    # the family's tree has been optimised once, every set_tris refits that topology
+    dynamic_refit = None
+    if world == 1 and per_frame_rebuild:
+        from portablert_b200 import scenes as _sc
+        frames = [torch.from_numpy(_sc.heightfield(f)).to(dev) for f in range(4)]
+        backend.set_tree_optimisation(3, passes)
+        backend.set_tris_dev(frames[0].data_ptr(), n_tris)
+        r0 = backend.refits
+        k = 0
+        while backend.refits < r0 + 3 and k < 24:  # until the family is optimised and refits have begun
+            k += 1
+            backend.set_tris_dev(frames[k % 4].data_ptr(), n_tris)
+            backend.trace_dev(d_rays.data_ptr(), n_rays, mask, **outs)
+        r1, j1 = backend.refits, backend.refit_rejects
+        b_ms, t_ms = [], []
+        for i in range(max(args.steps, 8)):
+            l2_flush()
+            b_ms.append(backend.set_tris_dev(frames[(k + 1 + i) % 4].data_ptr(), n_tris))
+            l2_flush()
+            t_ms.append(backend.trace_dev(d_rays.data_ptr(), n_rays, mask, **outs))
+        dynamic_refit = {
+            "set_tris_ms": float(np.mean(b_ms)), "trace_ms": float(np.mean(t_ms)),
+            "frame_ms": float(np.mean(b_ms) + np.mean(t_ms)),
+            "default_frame_ms": build_ms_mean + ms_per_step,
+            "value": n_rays / (float(np.mean(t_ms)) * 1e-3) / 1e6, "unit": "Mrays/s",
+            "refits": backend.refits - r1, "rebuilds": backend.refit_rejects - j1,
+            "warmup_frames": k, "tree_height": backend.tree_depth,
+            "note": "PRT_B200_TREELET_MODE=3: 4 distinct frames of the height field (phase 0.1*f) in "
+                    "rotation; set_tris refits the optimised topology (1 kernel + SAH check)"}
+        backend.set_tree_optimisation(int(os.environ.get("PRT_B200_TREELET_MODE", "2")), passes)
+        backend.set_tris_dev(d_tris.data_ptr(), n_tris)
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -630,7 +663,7 @@ def main():
                             % len(numa_cpus) if numa_cpus else "no NUMA binding")},
         "build_mtris_s": build["mtris_s"], "build": build,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": roofline, "cpu_baseline": cpu, "watertight": watertight,
+        "roofline": roofline, "cpu_baseline": cpu, "watertight": watertight, "dynamic_refit": dynamic_refit,
         "wall_s_timed_region": wall, "device": backend.device_name(),
     }
     if per_mask:

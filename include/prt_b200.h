@@ -138,6 +138,13 @@ int prt_b200_set_trace_opts(prt_b200 *ctx, const prt_trace_opts *opts);
  *           -- about when tracing the plain tree has cost what the optimisation costs -- it is
  *           optimised before the next batch is traced; a scene rebuilt every frame (config C5)
  *           never pays for it, a static one pays once
+ *   mode 3  (opt-in) mode 2 plus temporal reuse for deforming meshes: rays are counted per scene
+ *           FAMILY (consecutive set_tris calls with the same triangle count), and once the family's
+ *           tree has been optimised, the next set_tris of that size refits the optimised topology
+ *           to the new vertices (one kernel) instead of rebuilding.  The refitted tree is kept only
+ *           if its SAH cost stays within 1.25x of the cost it had when optimised; otherwise the
+ *           scene is rebuilt and optimised at once.  Results never depend on it: every box is the
+ *           exact union of what is below.  prt_b200_refits / prt_b200_refit_rejects count both cases.
  * passes: 1..8 (default 2).  Env PRT_B200_TREELET_MODE / PRT_B200_TREELET_PASSES.
  * prt_b200_tree_depth: height of the optimised tree (0 = the current tree is the plain radix tree);
  * prt_b200_last_optimise_ms: device time the lazy optimisation of the current scene took.
@@ -148,6 +155,8 @@ int prt_b200_set_tree_optimisation(prt_b200 *ctx, int mode, int passes);
 int32_t prt_b200_tree_depth(const prt_b200 *ctx);
 float prt_b200_last_optimise_ms(const prt_b200 *ctx);
 uint64_t prt_b200_strict_fallbacks(const prt_b200 *ctx);
+uint64_t prt_b200_refits(const prt_b200 *ctx);
+uint64_t prt_b200_refit_rejects(const prt_b200 *ctx);
 
 /* Triangle test: 0 (default) = the reference's Moeller-Trumbore arithmetic replayed operation for
  * operation (core.hpp:27-65) -- results identical to the reference CPU backend; 1 = opt-in

@@ -49,6 +49,8 @@ SYMBOLS = {
     "prt_b200_tree_depth": (C.c_int32, [C.c_void_p]),
     "prt_b200_last_optimise_ms": (C.c_float, [C.c_void_p]),
     "prt_b200_strict_fallbacks": (C.c_uint64, [C.c_void_p]),
+    "prt_b200_refits": (C.c_uint64, [C.c_void_p]),
+    "prt_b200_refit_rejects": (C.c_uint64, [C.c_void_p]),
     "prt_b200_set_triangle_test": (C.c_int, [C.c_void_p, C.c_int]),
     "prt_b200_triangle_test": (C.c_int, [C.c_void_p]),
     "prt_b200_set_ray_sorting": (C.c_int, [C.c_void_p, C.c_int]),

@@ -162,7 +162,7 @@ class CUDABackend(Backend):
     def set_tree_optimisation(self, mode: int, passes: int = 2):
         """SAH optimisation of the LBVH by treelet restructuring (Karras & Aila 2013): mode 0 never,
         1 inside every set_tris, 2 (default) lazily once a scene has served max(32 rays per triangle,
-        8 Mi rays)."""
+        8 Mi rays), 3 like 2 plus temporal reuse: frames of the same size refit the optimised topology."""
         self._need()
         self._check(lib().prt_b200_set_tree_optimisation(self._h, int(mode), int(passes)))
 
@@ -171,6 +171,17 @@ class CUDABackend(Backend):
         """height of the optimised tree; 0 while the current tree is the plain radix tree"""
         self._need()
         return int(lib().prt_b200_tree_depth(self._h))
+
+    @property
+    def refits(self) -> int:
+        """set_tris calls served by refitting the optimised topology (mode 3)"""
+        self._need()
+        return int(lib().prt_b200_refits(self._h))
+
+    @property
+    def refit_rejects(self) -> int:
+        self._need()
+        return int(lib().prt_b200_refit_rejects(self._h))
 
     @property
     def strict_fallbacks(self) -> int:

@@ -142,7 +142,7 @@ int prt_b200_create(prt_b200 **out, int device) {
 	if (const char *e = std::getenv("PRT_B200_FAST_BOXES"))
 		c->fast_boxes = std::atoi(e) != 0;
 	if (const char *e = std::getenv("PRT_B200_TREELET_MODE"))
-		c->optimise_mode = std::max(0, std::min(2, std::atoi(e)));
+		c->optimise_mode = std::max(0, std::min(3, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_MAX_TREE_DEPTH")) // tests: force the strict fallback
 		c->max_tree_depth = std::max(1, std::min(96, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_TREELET_PASSES"))
@@ -231,8 +231,8 @@ int prt_b200_set_wide_nodes(prt_b200 *c, int mode) {
 }
 
 int prt_b200_set_tree_optimisation(prt_b200 *c, int mode, int passes) {
-	if (!c || mode < 0 || mode > 2 || passes < 1 || passes > 8)
-		return fail(c, PRT_E_ARG, "set_tree_optimisation: mode must be 0..2 and passes 1..8");
+	if (!c || mode < 0 || mode > 3 || passes < 1 || passes > 8)
+		return fail(c, PRT_E_ARG, "set_tree_optimisation: mode must be 0..3 and passes 1..8");
 	c->optimise_mode = mode;
 	c->optimise_passes = passes;
 	return PRT_OK;
@@ -240,6 +240,8 @@ int prt_b200_set_tree_optimisation(prt_b200 *c, int mode, int passes) {
 int32_t prt_b200_tree_depth(const prt_b200 *c) { return c ? c->tree_depth : 0; }
 float prt_b200_last_optimise_ms(const prt_b200 *c) { return c ? c->last_optimise_ms : 0.f; }
 uint64_t prt_b200_strict_fallbacks(const prt_b200 *c) { return c ? c->strict_fallbacks : 0; }
+uint64_t prt_b200_refits(const prt_b200 *c) { return c ? c->refits : 0; }
+uint64_t prt_b200_refit_rejects(const prt_b200 *c) { return c ? c->refit_rejects : 0; }
 
 int prt_b200_set_triangle_test(prt_b200 *c, int mode) {
 	if (!c || mode < 0 || mode > 1)
@@ -270,9 +272,16 @@ int prt_b200_set_trace_opts(prt_b200 *c, const prt_trace_opts *o) {
 static int timed_build(prt_b200 *c, const float *d_tris9, uint64_t n, float *ms) {
 	PRT_CUDA(c, cudaSetDevice(c->device));
 	PRT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-	int rc = prt::build_lbvh(c, d_tris9, n);
+	bool reused = false;
+	int rc = prt::try_reuse_topology(c, d_tris9, n, c->stream, &reused);
 	if (rc)
 		return rc;
+	if (!reused) {
+		rc = prt::build_lbvh(c, d_tris9, n);
+		c->force_eager = false;
+		if (rc)
+			return rc;
+	}
 	PRT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
 	// root index + scene box (fast box test margin, ray-sort grid), published by the build
 	struct {

@@ -645,6 +645,94 @@ __global__ void __launch_bounds__(TL_THREADS)
 }
 
 // ------------------------------------------------------------------------------------------------
+// 5c. temporal reuse (opt-in, mode 3): a new frame of a deforming mesh keeps the optimised topology
+// ------------------------------------------------------------------------------------------------
+// One thread per leaf: rewrite the triangle record from the new vertices (tris9 == nullptr: keep
+// the records, just measure), then climb like the hierarchy kernel does -- write this subtree's box
+// into its half of the parent, one arrival counter per node, the second arrival carries the union
+// upwards -- but along the stored parent links of the existing topology.  Every box is again the
+// exact union of what is below it, so results cannot depend on whether a frame was refitted or
+// rebuilt; only the quality of the tree can, which is why the summed surface area of the internal
+// nodes (the SAH cost, up to constants) is measured on the way: sah[0..63] partial sums, sah[64]
+// the root's area.
+__global__ void __launch_bounds__(256)
+    k_refit(const float *__restrict__ tris9, int n, TriRec *recs, Node *nodes,
+            const int32_t *__restrict__ parent, const int32_t *__restrict__ leaf_parent, unsigned *flag,
+            RootInfo *root_info, float *sah, bool vertex_form) {
+	const int j = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+	if (j >= n)
+		return;
+	Box b;
+	float4 *rec = reinterpret_cast<float4 *>(recs + j);
+	if (tris9) {
+		const uint32_t prim = __float_as_uint(rec[0].w);
+		const float *src = tris9 + (uint64_t)prim * 9;
+		float t[9];
+#pragma unroll
+		for (int k = 0; k < 9; ++k)
+			t[k] = __ldg(src + k);
+		b = tri_box(t);
+		rec[0] = make_float4(t[0], t[1], t[2], __uint_as_float(prim));
+		if (vertex_form) {
+			rec[1] = make_float4(t[3], t[4], t[5], b.lo[0]);
+			rec[2] = make_float4(t[6], t[7], t[8], b.lo[1]);
+		} else { // edges exactly as core.hpp:33-35 computes them
+			rec[1] = make_float4(fsub(t[3], t[0]), fsub(t[4], t[1]), fsub(t[5], t[2]), b.lo[0]);
+			rec[2] = make_float4(fsub(t[6], t[0]), fsub(t[7], t[1]), fsub(t[8], t[2]), b.lo[1]);
+		}
+		rec[3] = make_float4(b.lo[2], b.hi[0], b.hi[1], b.hi[2]);
+	} else {
+		const float4 r1 = rec[1], r2 = rec[2], r3 = rec[3];
+		b.lo[0] = r1.w;
+		b.lo[1] = r2.w;
+		b.lo[2] = r3.x;
+		b.hi[0] = r3.y;
+		b.hi[1] = r3.z;
+		b.hi[2] = r3.w;
+	}
+	const int32_t root = root_info->root;
+	int32_t me = ~j, cur = leaf_parent[j];
+	float acc = 0.0f;
+	for (;;) {
+		const int4 tail = __ldg(reinterpret_cast<const int4 *>(nodes + cur) + 3); // topology is fixed
+		const int side = tail.y == me ? 1 : 0;
+		float2 *nd = reinterpret_cast<float2 *>(nodes + cur) + (side ? 3 : 0);
+		nd[0] = make_float2(b.lo[0], b.lo[1]);
+		nd[1] = make_float2(b.lo[2], b.hi[0]);
+		nd[2] = make_float2(b.hi[1], b.hi[2]);
+		__threadfence();
+		if (atomicAdd(flag + cur, 1u) == 0u)
+			break;
+		__threadfence();
+		const float2 *sib = reinterpret_cast<const float2 *>(nodes + cur) + (side ? 0 : 3);
+		const float2 s0 = __ldcg(sib), s1 = __ldcg(sib + 1), s2 = __ldcg(sib + 2);
+		Box o;
+		o.lo[0] = s0.x;
+		o.lo[1] = s0.y;
+		o.lo[2] = s1.x;
+		o.hi[0] = s1.y;
+		o.hi[1] = s2.x;
+		o.hi[2] = s2.y;
+		b = side ? box_union(o, b) : box_union(b, o); // always (child0, child1)
+		const float area = box_half_area(b);
+		acc += area;
+		if (cur == root) {
+#pragma unroll
+			for (int a = 0; a < 3; ++a) {
+				root_info->lo[a] = b.lo[a];
+				root_info->hi[a] = b.hi[a];
+			}
+			sah[64] = area;
+			break;
+		}
+		me = cur;
+		cur = parent[cur];
+	}
+	if (acc != 0.0f)
+		atomicAdd(sah + (threadIdx.x & 63), acc);
+}
+
+// ------------------------------------------------------------------------------------------------
 // 6. compressed 4-wide nodes: wide node i = the grandchildren of binary node i, 8-bit boxes
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ Node load_node(const Node *nodes, int32_t i) {
@@ -731,6 +819,56 @@ static int treelet_passes(prt_b200 *c, cudaStream_t s, int passes, bool strict) 
 	return PRT_OK;
 }
 
+// Refit the current topology to new (or, tris9 == nullptr, the current) triangles and measure the
+// SAH cost of the result: *sah_out = summed half areas of the internal nodes / the root's.
+// Needs the parent links of the current tree (tl_parent / tl_leaf_parent).  Synchronises `s`.
+static int refit_tree(prt_b200 *c, const float *d_tris9, cudaStream_t s, double *sah_out) {
+	const uint64_t n = c->n_tris;
+	PRT_CUDA(c, c->tl_sah.reserve(65 * 4));
+	PRT_CUDA(c, cudaMemsetAsync(c->tl_sah.p, 0, 65 * 4, s));
+	PRT_CUDA(c, cudaMemsetAsync(c->tl_flag.p, 0, (n - 1) * 4, s));
+	k_refit<<<(int)((n + 255) / 256), 256, 0, s>>>(
+	    d_tris9, (int)n, c->trirecs.as<TriRec>(), c->nodes.as<Node>(), c->tl_parent.as<int32_t>(),
+	    c->tl_leaf_parent.as<int32_t>(), c->tl_flag.as<unsigned>(), c->root_info.as<RootInfo>(),
+	    c->tl_sah.as<float>(), c->recs_vertex_form);
+	c->launches += 1;
+	float h[65];
+	PRT_CUDA(c, cudaMemcpyAsync(h, c->tl_sah.p, sizeof h, cudaMemcpyDeviceToHost, s));
+	PRT_CUDA(c, cudaStreamSynchronize(s));
+	double sum = 0.0;
+	for (int k = 0; k < 64; ++k)
+		sum += h[k];
+	*sah_out = h[64] > 0.0f ? sum / h[64] : INFINITY;
+	return PRT_OK;
+}
+
+// Mode 3: set_tris with as many triangles as the current, optimised scene first tries the
+// previous topology (a deforming mesh keeps its connectivity and most of its shape); the refitted
+// tree is accepted if its SAH cost stays within REFIT_TOLERANCE of the cost it had when it was
+// optimised, otherwise the caller rebuilds (and, the scene family having proven itself worth it,
+// optimises right away).  *reused says which.
+int try_reuse_topology(prt_b200 *c, const float *d_tris9, uint64_t n, cudaStream_t s, bool *reused) {
+	*reused = false;
+	c->force_eager = false;
+	if (c->optimise_mode != 3 || !c->topology_valid || !c->tree_optimised || n != c->n_tris ||
+	    c->recs_vertex_form != (c->watertight != 0))
+		return PRT_OK;
+	double sah = 0.0;
+	if (int rc = refit_tree(c, d_tris9, s, &sah))
+		return rc;
+	if (sah <= c->sah_ref * REFIT_TOLERANCE) {
+		if (int rc = build_wide(c, s))
+			return rc;
+		c->refits++;
+		c->last_sah = sah;
+		*reused = true;
+	} else {
+		c->refit_rejects++;
+		c->force_eager = true;
+	}
+	return PRT_OK;
+}
+
 // SAH optimisation of the current tree, in place (5b).  The restructured tree is measured: should it
 // come out taller than the traversal stack is sized for, the saved radix tree is restored and
 // optimised again under the height-preserving rule (treelet_commit: strict).  Synchronises `s`.
@@ -763,6 +901,16 @@ int optimise_tree(prt_b200 *c, cudaStream_t s) {
 	}
 	c->tree_depth = depth;
 	c->tree_optimised = true;
+	if (c->optimise_mode == 3) { // links of the FINAL topology and its cost: the yardstick for refits
+		k_parents<<<(int)((n - 1 + 255) / 256), 256, 0, s>>>(c->nodes.as<Node>(), (int)(n - 1),
+		                                                    c->tl_parent.as<int32_t>(),
+		                                                    c->tl_leaf_parent.as<int32_t>());
+		c->launches += 1;
+		if (int rc = refit_tree(c, nullptr, s, &c->sah_ref))
+			return rc;
+		c->last_sah = c->sah_ref;
+		c->topology_valid = true;
+	}
 	return PRT_OK;
 }
 
@@ -775,7 +923,7 @@ int optimise_tree(prt_b200 *c, cudaStream_t s) {
 // by the trace entry points (api.cu) before they launch anything.
 int maybe_optimise_tree(prt_b200 *c, uint64_t n_rays) {
 	c->rays_since_build += n_rays;
-	if (c->optimise_mode != 2 || c->tree_optimised || c->n_tris < (uint64_t)TREELET_N ||
+	if (c->optimise_mode < 2 || c->tree_optimised || c->n_tris < (uint64_t)TREELET_N ||
 	    c->rays_since_build < std::max<uint64_t>(LAZY_RAYS_PER_TRI * c->n_tris, LAZY_MIN_RAYS))
 		return PRT_OK;
 	cudaStream_t s = c->stream;
@@ -809,12 +957,15 @@ static int morton_bits_for(uint64_t n) {
 
 int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 	cudaStream_t s = c->stream;
+	// (mode 3 counts the rays of a scene FAMILY: frames of the same size keep the counter)
+	if (!(c->optimise_mode == 3 && n == c->n_tris))
+		c->rays_since_build = 0;
 	c->n_tris = n;
 	c->n_nodes = n == 0 ? 0 : (n == 1 ? 1 : n - 1);
 	c->wide_built = false;
 	c->tree_optimised = false;
+	c->topology_valid = false;
 	c->tree_depth = 0;
-	c->rays_since_build = 0;
 	c->last_optimise_ms = 0.f;
 	c->recs_vertex_form = c->watertight != 0;
 	const bool vf = c->recs_vertex_form;
@@ -865,7 +1016,7 @@ int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 		                              c->bound.as<int>(), c->root_info.as<RootInfo>(), vf);
 		c->launches += 1;
 	}
-	if (c->optimise_mode == 1) // inside every set_tris
+	if (c->optimise_mode == 1 || c->force_eager) // inside every set_tris / a rejected refit
 		if (int rc = optimise_tree(c, s))
 			return rc;
 	c->wide_built = !vf && (c->wide_mode == 1 || (c->wide_mode == 2 && n >= (1ull << 20)));

@@ -90,10 +90,13 @@ struct prt_b200 {
 	// build scratch
 	prt::DevBuf keys[2], vals[2], sort_scratch, bounds, leaf_box, bound, root_info;
 	// opt-in treelet SAH optimisation (build.cu 5b): parent links, arrival flags, leaf counts, heights
-	prt::DevBuf tl_parent, tl_leaf_parent, tl_flag, tl_count, tl_depth, tl_backup;
-	int optimise_mode = 2;   // env PRT_B200_TREELET_MODE: 0 never, 1 inside set_tris, 2 lazily (default)
+	prt::DevBuf tl_parent, tl_leaf_parent, tl_flag, tl_count, tl_depth, tl_backup, tl_sah;
+	int optimise_mode = 2;   // env PRT_B200_TREELET_MODE: 0 never, 1 inside set_tris, 2 lazily (default), 3 lazily + temporal reuse
 	int optimise_passes = 2; // env PRT_B200_TREELET_PASSES
 	bool tree_optimised = false;
+	bool topology_valid = false, force_eager = false; // mode 3: parent links match the nodes / rebuild optimises at once
+	double sah_ref = 0.0, last_sah = 0.0;             // mode 3: SAH cost when optimised / after the last refit
+	uint64_t refits = 0, refit_rejects = 0;
 	uint64_t rays_since_build = 0, strict_fallbacks = 0;
 	int max_tree_depth = 96; // what prt_traverse.cuh: STACK_DEPTH is sized for (env PRT_B200_MAX_TREE_DEPTH: tests)
 	float last_optimise_ms = 0.f; // device time of the lazy optimisation of the current scene (0 = none yet)
@@ -154,7 +157,9 @@ inline int fail(prt_b200 *c, int code, const char *what, cudaError_t e = cudaSuc
 constexpr uint64_t LAZY_RAYS_PER_TRI = 32;  // lazy tree optimisation threshold: max(32 rays per
 constexpr uint64_t LAZY_MIN_RAYS = 8u << 20; // triangle, 8 Mi rays) since the last set_tris
 int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n);
+constexpr double REFIT_TOLERANCE = 1.25;     // mode 3: accepted growth of the SAH cost under refitting
 int optimise_tree(prt_b200 *c, cudaStream_t s);
+int try_reuse_topology(prt_b200 *c, const float *d_tris9, uint64_t n, cudaStream_t s, bool *reused);
 int maybe_optimise_tree(prt_b200 *c, uint64_t n_rays);
 // trace.cu
 struct TraceOut {

@@ -29,6 +29,7 @@ class Emu:
         L.emu_load.restype = C.c_void_p
         L.emu_load.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int32]
         L.emu_free.argtypes = [C.c_void_p]
+        L.emu_refit.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.emu_treelet.restype = C.c_int32
         L.emu_treelet.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
         L.emu_num_nodes.restype = C.c_uint64
@@ -60,6 +61,13 @@ class Emu:
         ch = C.c_uint64(0)
         d = self.L.emu_treelet(self.h, int(passes), int(strict), C.byref(ch))
         return int(d), int(ch.value)
+
+    def refit(self, tris, watertight=False):
+        """same topology, new vertices (stand-in for k_refit)"""
+        tris = np.ascontiguousarray(tris, np.float32).reshape(-1, 9)
+        assert len(tris) == self.n
+        self.L.emu_refit(self.h, tris.ctypes.data, int(watertight))
+        return self
 
     def free(self):
         if self.h:

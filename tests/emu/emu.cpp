@@ -124,6 +124,32 @@ int32_t emu_treelet(void *h, int passes, int strict, uint64_t *changed) {
 	return d;
 }
 
+// sequential stand-in for k_refit (build.cu): same topology, new vertices
+void emu_refit(void *h, const float *tris9, int vertex_form) {
+	Emu *e = static_cast<Emu *>(h);
+	if (e->n < 2)
+		return;
+	std::vector<Box> leaf(e->n);
+	for (uint64_t j = 0; j < e->n; ++j) {
+		TriRec &r = e->tris[j];
+		const float *t = tris9 + 9ull * r.prim;
+		leaf[j] = tri_box(t);
+		for (int a = 0; a < 3; ++a) {
+			r.v0[a] = t[a];
+			r.e1[a] = vertex_form ? t[3 + a] : t[3 + a] - t[a];
+			r.e2[a] = vertex_form ? t[6 + a] : t[6 + a] - t[a];
+		}
+		r.lox = leaf[j].lo[0];
+		r.loy = leaf[j].lo[1];
+		r.loz = leaf[j].lo[2];
+		r.hix = leaf[j].hi[0];
+		r.hiy = leaf[j].hi[1];
+		r.hiz = leaf[j].hi[2];
+	}
+	refit(*e, leaf, e->root);
+	e->bounds();
+}
+
 void *emu_build(const float *tris9, uint64_t n, int bits, int vertex_form) {
 	Emu *e = new Emu();
 	e->n = n;

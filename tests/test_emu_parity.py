@@ -354,3 +354,23 @@ def test_treelet_optimisation_survives_degenerate_triangles(emu):
         for k in ("valid", "t", "pid", "u", "v"):
             assert np.array_equal(after[k], before[k], equal_nan=True), k
     assert np.array_equal(emu.trace(rays, wide=True)["t"], before["t"], equal_nan=True)
+
+
+def test_refit_keeps_results_exact_on_a_deforming_mesh(oracle, emu):
+    """temporal reuse (mode 3): the optimised topology of frame 0 refitted to later frames stays a
+    valid tree with exact boxes and gives the oracle's answers for those frames"""
+    from bvhcheck import sah_internal_area
+    rays = scenes.camera_rays(80, 60, (10, 6, -4), (10, 0, 5))
+    f0 = scenes.heightfield(frame=0, nx=60, nz=40)
+    emu.build(f0, 10)
+    emu.treelet(2)
+    base = sah_internal_area(emu.download()[0])
+    for frame in (1, 2, 5):
+        tris = scenes.heightfield(frame=frame, nx=60, nz=40)
+        emu.refit(tris)
+        nodes, recs = emu.download()
+        check_bvh(nodes, recs, tris)
+        rep = parity.compare(oracle.build(tris).trace(rays), emu.trace(rays), tris, rays, oracle)
+        parity.assert_parity(rep)
+        assert rep["t_bitexact"]
+        print("frame", frame, "SAH", round(sah_internal_area(nodes), 2), "vs", round(base, 2), "when optimised")
