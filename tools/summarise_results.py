@@ -61,6 +61,13 @@ def main():
         if pm:
             out.append("C2, all 31 tag combinations (device-timed Mrays/s): " +
                        ", ".join(f"{k} {v:.0f}" for k, v in pm.items()) + "\n")
+    d5 = load("bench_c5.json")
+    if d5 and d5.get("dynamic_refit"):
+        r = d5["dynamic_refit"]
+        out.append(f"C5 with temporal reuse (opt-in mode 3; 4 distinct frames of the deforming height field in "
+                   f"rotation): set_tris {r['set_tris_ms']:.3f} ms (refit), traversal {r['trace_ms']:.3f} ms "
+                   f"({r['value']:.0f} Mrays/s), frame {r['frame_ms']:.3f} ms vs {r['default_frame_ms']:.3f} ms with "
+                   f"the default per-frame rebuild; {r['refits']} refits, {r['rebuilds']} rebuilds in the timed frames.\n")
     out.append("Opt-in watertight triangle test beside the default (same rays, same tree state): "
                "Mrays/s, rays whose `valid` differs, rays whose t differs by more than 1e-5 relative:\n")
     out.append("| config | default Mrays/s | watertight Mrays/s | valid differs | t differs > 1e-5 rel |")
