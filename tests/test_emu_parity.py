@@ -374,3 +374,19 @@ def test_refit_keeps_results_exact_on_a_deforming_mesh(oracle, emu):
         parity.assert_parity(rep)
         assert rep["t_bitexact"]
         print("frame", frame, "SAH", round(sah_internal_area(nodes), 2), "vs", round(base, 2), "when optimised")
+
+
+@pytest.mark.parametrize("name", ["interior.npz", "heightfield.npz"])
+def test_kernel_source_matches_the_reference_fixtures_before_and_after_optimisation(name, oracle, emu):
+    """the committed outputs of the unmodified reference (tools/make_golden.py) vs the kernel source
+    driven on the host, on the plain radix tree and on the treelet-optimised one"""
+    g = golden(name)
+    ref = parity.from_structured(g["hits"])
+    oracle.build(g["tris"])
+    emu.build(g["tris"], 13)
+    for stage in ("plain", "optimised"):
+        got = emu.trace(g["rays"])
+        rep = parity.compare(ref, got, g["tris"], g["rays"], oracle)
+        parity.assert_parity(rep)
+        assert rep["t_equal"] and rep["u_maxabs"] == 0 and rep["v_maxabs"] == 0, (stage, rep)
+        emu.treelet(2)

@@ -49,7 +49,7 @@ def test_golden_kat_and_probes(oracle):
     assert h["tie_two_identical"]["primitive_id"] == 1 and h["tie_far_near_near"]["primitive_id"] == 2
 
 
-@pytest.mark.parametrize("name", ["bunny.npz", "soup.npz"])
+@pytest.mark.parametrize("name", ["bunny.npz", "soup.npz", "interior.npz", "heightfield.npz"])
 def test_golden_scenes(oracle, name):
     g = golden(name)
     oracle.build(g["tris"])

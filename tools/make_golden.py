@@ -16,6 +16,9 @@ Contents
   c1.npz           config C1: every 16th of the 1 M rays, reference t
   c2.npz           config C2: every 53rd of the 1920x1080 rays on the 69 192-triangle blob, all tags
   soup.npz         random overlapping triangle soup with negative-t hits, all tags
+  interior.npz     C3-style interior (8 000 triangles: large walls + small detail), 192x108 primary rays
+  heightfield.npz  C5-style height field (frame 3, 4 800 triangles), 192x108 primary rays
+(`python tools/make_golden.py interior heightfield` regenerates only the named ones)
 """
 import hashlib
 import os
@@ -119,9 +122,29 @@ def main():
     print("soup: valid", h["valid"].mean(), "negative t", (h["t"] < 0).sum())
     np.savez_compressed(os.path.join(OUT, "soup.npz"), tris=soup, rays=rays, hits=h)
 
+    extra_scenes(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+def extra_scenes(ref, only=None):
+    """C3- and C5-style scenes at fixture size: triangles, rays and the reference's full records"""
+    todo = {
+        "interior": (scenes.interior(8000), scenes.camera_rays(192, 108, (2, 6, 3), (28, 4, 15))),
+        "heightfield": (scenes.heightfield(frame=3, nx=60, nz=40),
+                        scenes.camera_rays(192, 108, (10, 6, -4), (10, 0, 5))),
+    }
+    for name, (tris, rays) in todo.items():
+        if only and name not in only:
+            continue
+        ref.set_tris(tris)
+        h = full(ref, rays)
+        print(name, len(tris), "tris, valid", h["valid"].mean())
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), tris=tris, rays=rays, hits=h)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1:
+        extra_scenes(Reference(), only=set(sys.argv[1:]))
+    else:
+        main()
