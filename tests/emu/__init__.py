@@ -30,6 +30,8 @@ class Emu:
         L.emu_load.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int32]
         L.emu_free.argtypes = [C.c_void_p]
         L.emu_refit.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.emu_check_split_search.restype = C.c_int
+        L.emu_check_split_search.argtypes = [C.c_void_p]
         L.emu_treelet.restype = C.c_int32
         L.emu_treelet.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
         L.emu_num_nodes.restype = C.c_uint64
@@ -61,6 +63,11 @@ class Emu:
         ch = C.c_uint64(0)
         d = self.L.emu_treelet(self.h, int(passes), int(strict), C.byref(ch))
         return int(d), int(ch.value)
+
+    def check_split_search(self, copt):
+        copt = np.ascontiguousarray(copt, np.float32)
+        assert copt.size == 128
+        return int(self.L.emu_check_split_search(copt.ctypes.data))
 
     def refit(self, tris, watertight=False):
         """same topology, new vertices (stand-in for k_refit)"""

@@ -124,6 +124,57 @@ int32_t emu_treelet(void *h, int passes, int strict, uint64_t *changed) {
 	return d;
 }
 
+// The split searches the device kernel spreads over lanes (treelet_best_split_quarter for 4 lanes
+// per subset, direct indexing p = 2(i+1) for the full set, merged on the key (cost, split)) must
+// select exactly what the sequential recurrence selects.  copt: TREELET_SETS costs (any values,
+// ties and infinities included).  Returns the number of subsets on which they disagree.
+int emu_check_split_search(const float *copt) {
+	int bad = 0;
+	for (int s = 1; s < TREELET_SETS; ++s) {
+		if ((s & (s - 1)) == 0)
+			continue;
+		float want;
+		int want_p;
+		treelet_best_split(copt, s, 0, 1, want, want_p);
+		float best = INFINITY;
+		int bp = 0xff;
+		for (int sub = 0; sub < 4; ++sub) { // lanes merge with: smaller cost, then smaller split
+			float b;
+			int p;
+			treelet_best_split_quarter(copt, s, sub, b, p);
+			if (b < best || (b == best && p < bp)) {
+				best = b;
+				bp = p;
+			}
+		}
+		bad += !(bp == want_p && (best == want || (bp == 0xff)));
+		if (s == TREELET_SETS - 1) { // the full set as the kernel indexes it
+			float fb = INFINITY;
+			int fp = 0xff;
+			for (int lane = 0; lane < 32; ++lane) {
+				float lb = INFINITY;
+				int lp = 0xff;
+				for (int i = 0; i < 2; ++i) {
+					const int p = (lane + 32 * i + 1) << 1;
+					if (p < s) {
+						const float c = copt[p] + copt[s ^ p];
+						if (c < lb) {
+							lb = c;
+							lp = p;
+						}
+					}
+				}
+				if (lb < fb || (lb == fb && lp < fp)) {
+					fb = lb;
+					fp = lp;
+				}
+			}
+			bad += !(fp == want_p && (fb == want || fp == 0xff));
+		}
+	}
+	return bad;
+}
+
 // sequential stand-in for k_refit (build.cu): same topology, new vertices
 void emu_refit(void *h, const float *tris9, int vertex_form) {
 	Emu *e = static_cast<Emu *>(h);

@@ -390,3 +390,20 @@ def test_kernel_source_matches_the_reference_fixtures_before_and_after_optimisat
         parity.assert_parity(rep)
         assert rep["t_equal"] and rep["u_maxabs"] == 0 and rep["v_maxabs"] == 0, (stage, rep)
         emu.treelet(2)
+
+
+def test_lane_parallel_split_search_equals_the_sequential_recurrence(emu):
+    """k_treelet splits the search for the best partition of a leaf subset over lanes (four per
+    6-leaf subset, all 32 for the full set, merged on (cost, split)); for any cost table -- random,
+    heavily tied, with infinities and NaNs -- that must select what treelet_dp selects."""
+    g = np.random.default_rng(9)
+    tables = [g.random(128, dtype=np.float32) for _ in range(200)]
+    tables += [np.round(g.random(128) * 3).astype(np.float32) for _ in range(200)]  # many ties
+    tables += [np.zeros(128, np.float32), np.full(128, np.inf, np.float32)]
+    for _ in range(50):
+        t = g.random(128, dtype=np.float32)
+        t[g.integers(0, 128, 20)] = np.inf
+        t[g.integers(0, 128, 5)] = np.nan
+        tables.append(t)
+    for t in tables:
+        assert emu.check_split_search(t) == 0
