@@ -928,8 +928,16 @@ int maybe_optimise_tree(prt_b200 *c, uint64_t n_rays) {
 		return PRT_OK;
 	cudaStream_t s = c->stream;
 	PRT_CUDA(c, cudaEventRecord(c->ev0, s));
-	if (int rc = optimise_tree(c, s))
-		return rc;
+	if (int rc = optimise_tree(c, s)) {
+		if (rc != PRT_E_OOM)
+			return rc;
+		// no room for the scratch (it is reserved before anything is touched): the optimisation is
+		// optional, the plain tree stays in place and the trace goes on
+		cudaGetLastError();
+		c->tree_optimised = true;
+		c->err.clear();
+		return PRT_OK;
+	}
 	if (int rc = build_wide(c, s))
 		return rc;
 	PRT_CUDA(c, cudaEventRecord(c->ev1, s));
