@@ -315,41 +315,59 @@ def main():
             build_ms.append(ms)
     # the same build with the tree optimisation inside set_tris (mode 1): what a static scene pays in
     # total, measured with all scratch allocated (the lazy default runs the same kernels later)
-    passes = int(os.environ.get("PRT_B200_TREELET_PASSES", "2"))
-    backend.set_tree_optimisation(1, passes)
+    tl_mode = int(os.environ.get("PRT_B200_TREELET_MODE", "3"))
+    tl_passes = int(os.environ.get("PRT_B200_TREELET_PASSES", "2"))
+    backend.set_tree_optimisation(1, tl_passes)
     build_opt_ms = []
     for k in range(3 + min(args.steps, 10)):
         l2_flush()
         ms = backend.set_tris_dev(d_tris.data_ptr(), n_tris)
         if k >= 3:
             build_opt_ms.append(ms)
-    backend.set_tree_optimisation(int(os.environ.get("PRT_B200_TREELET_MODE", "2")), passes)
+    backend.set_tree_optimisation(tl_mode, tl_passes)
     backend.set_tris_dev(d_tris.data_ptr(), n_tris)
 
     # ---- traversal: W warm-up + exactly K timed steps
-    # C5 is the dynamic scene: every frame rebuilds the BVH (set_tris) and traces it once, so each
-    # step runs on a freshly built tree (the rebuild itself is the `build` figure, not part of the
-    # traversal time).  The other configs are static scenes traced repeatedly: the library
-    # optimises their tree lazily (treelet restructuring) once they have served max(32 rays per
-    # triangle, 8 Mi rays); the warm-up is extended until that has happened, so the timed steps
-    # show the steady state, and the one-off cost is reported as build.optimise_ms.
-    per_frame_rebuild = args.config == "c5"
+    # Static scenes (all configs but C5) are traced repeatedly: the library optimises their tree
+    # lazily (treelet restructuring) once they have served max(32 rays per triangle, 8 Mi rays).
+    # C5 is the dynamic scene: every step calls set_tris with the NEXT of four distinct frames of
+    # the deforming height field and traces it once; with the default temporal reuse the library,
+    # after the same lazy optimisation, refits the optimised topology in set_tris instead of
+    # rebuilding.  The warm-up is extended until that steady state is reached; the one-off costs
+    # and the per-frame set_tris time are reported under `build` (not part of the traversal time).
+    dynamic = args.config == "c5"
+    frames = [d_tris]
+    if dynamic:
+        from portablert_b200 import scenes as _sc
+        frames += [torch.from_numpy(_sc.heightfield(f)).to(dev) for f in (1, 2, 3)]
+    frame_no, set_tris_ms = [0], []
 
     def new_frame():
-        if per_frame_rebuild:
-            backend.set_tris_dev(d_tris.data_ptr(), n_tris)
+        if dynamic:
+            frame_no[0] += 1
+            set_tris_ms.append(backend.set_tris_dev(frames[frame_no[0] % len(frames)].data_ptr(), n_tris))
 
     for _ in range(args.warmup):
         new_frame()
         l2_flush()
         backend.trace_dev(d_rays.data_ptr(), n_rays, mask, **outs)
-    extra_warmup = 0
-    while (not per_frame_rebuild and backend.tree_depth == 0 and extra_warmup < 64
-           and os.environ.get("PRT_B200_TREELET_MODE", "2") == "2" and n_tris >= 7):
+    extra_warmup, refits0 = 0, backend.refits
+
+    def steady():
+        if n_tris < 7 or tl_mode < 2:
+            return True
+        if dynamic:
+            return tl_mode < 3 or backend.refits >= refits0 + 2
+        return backend.tree_depth > 0
+
+    while not steady() and extra_warmup < 64:
+        new_frame()
         l2_flush()
         backend.trace_dev(d_rays.data_ptr(), n_rays, mask, **outs)
         extra_warmup += 1
     optimise_ms, tree_depth = backend.last_optimise_ms, backend.tree_depth
+    set_tris_ms.clear()
+    refits1, rejects1 = backend.refits, backend.refit_rejects
     sampler = ClockSampler(local).start() if rank == 0 else None
     barrier()
     launches0 = backend.launch_count
@@ -361,7 +379,9 @@ def main():
         step_ms.append(backend.trace_dev(d_rays.data_ptr(), n_rays, mask, **outs))
     barrier()
     wall = time.perf_counter() - wall0
-    launches = backend.launch_count - launches0  # (C5: includes the per-frame rebuild's kernels)
+    launches = backend.launch_count - launches0  # (C5: includes the kernels of the per-frame set_tris)
+    steady_set_tris_ms = float(np.mean(set_tris_ms)) if set_tris_ms else None
+    refits_timed, rebuilds_timed = backend.refits - refits1, backend.refit_rejects - rejects1
     clocks = sampler.stop() if sampler else None
     dev_ms = float(np.sum(step_ms))
     if world > 1:
@@ -547,9 +567,14 @@ def main():
     build = {"mtris_s": n_tris / (build_ms_mean * 1e-3) / 1e6, "ms": build_ms_mean,
              "ms_with_optimisation": float(np.mean(build_opt_ms)),
              "mtris_s_with_optimisation": n_tris / (float(np.mean(build_opt_ms)) * 1e-3) / 1e6,
-             "optimise_passes": passes,
+             "optimise_passes": tl_passes,
              "first_lazy_optimise_ms": optimise_ms, "tree_height": tree_depth,
-             "tree": ("plain LBVH, rebuilt before every step (dynamic scene)" if per_frame_rebuild else
+             "set_tris_ms_steady": steady_set_tris_ms, "refits_in_timed_steps": refits_timed,
+             "rebuilds_in_timed_steps": rebuilds_timed,
+             "tree": (("deforming mesh, 4 distinct frames in rotation: after the lazy optimisation set_tris "
+                       "refits the optimised topology (temporal reuse, mode 3; `set_tris_ms_steady`); `ms` is "
+                       "a full rebuild of the plain LBVH" if refits_timed else
+                       "plain LBVH, rebuilt before every step (dynamic scene)") if dynamic else
                       "LBVH from set_tris (timed as `ms`), then optimised once by treelet "
                       "restructuring after max(32 rays per triangle, 8 Mi rays) (inside the warm-up, "
                       "which was extended by %d steps for it; `first_lazy_optimise_ms` includes "
@@ -581,6 +606,8 @@ def main():
     # many rays of this batch it answers differently
     watertight = None
     if world == 1 and mask & 2:
+        if dynamic:  # compare on one and the same frame
+            backend.set_tris_dev(d_tris.data_ptr(), n_tris)
         backend.trace_dev(d_rays.data_ptr(), n_rays, mask, **outs)
         t_def = t.clone()
         backend.set_triangle_test(1)
@@ -603,41 +630,30 @@ def main():
                       "t_rel_gt_1e-5": int((rel > 1e-5).sum().item()),
                       "note": "PRT_B200_WATERTIGHT=1 (Woop et al. 2013) vs the default on the same rays"}
         backend.set_triangle_test(0)
-        backend.set_tree_optimisation(int(os.environ.get("PRT_B200_TREELET_MODE", "2")),
-                                      int(os.environ.get("PRT_B200_TREELET_PASSES", "2")))
+        backend.set_tree_optimisation(tl_mode, tl_passes)
         backend.set_tris_dev(d_tris.data_ptr(), n_tris)
 
-    # ---- C5 with temporal reuse (opt-in mode 3): distinct frames of the deforming height field; after
-    # the family's tree has been optimised once, every set_tris refits that topology
-    dynamic_refit = None
-    if world == 1 and per_frame_rebuild:
-        from portablert_b200 import scenes as _sc
-        frames = [torch.from_numpy(_sc.heightfield(f)).to(dev) for f in range(4)]
-        backend.set_tree_optimisation(3, passes)
-        backend.set_tris_dev(frames[0].data_ptr(), n_tris)
-        r0 = backend.refits
-        k = 0
-        while backend.refits < r0 + 3 and k < 24:  # until the family is optimised and refits have begun
-            k += 1
-            backend.set_tris_dev(frames[k % 4].data_ptr(), n_tris)
-            backend.trace_dev(d_rays.data_ptr(), n_rays, mask, **outs)
-        r1, j1 = backend.refits, backend.refit_rejects
+    # ---- C5 without temporal reuse (mode 2), same frames: every set_tris rebuilds the plain LBVH
+    dynamic_plain = None
+    if world == 1 and dynamic:
+        backend.set_tree_optimisation(2, tl_passes)
         b_ms, t_ms = [], []
-        for i in range(max(args.steps, 8)):
+        for i in range(2 + max(args.steps, 8)):
             l2_flush()
-            b_ms.append(backend.set_tris_dev(frames[(k + 1 + i) % 4].data_ptr(), n_tris))
+            b = backend.set_tris_dev(frames[i % len(frames)].data_ptr(), n_tris)
             l2_flush()
-            t_ms.append(backend.trace_dev(d_rays.data_ptr(), n_rays, mask, **outs))
-        dynamic_refit = {
+            t_ = backend.trace_dev(d_rays.data_ptr(), n_rays, mask, **outs)
+            if i >= 2:
+                b_ms.append(b)
+                t_ms.append(t_)
+        dynamic_plain = {
             "set_tris_ms": float(np.mean(b_ms)), "trace_ms": float(np.mean(t_ms)),
             "frame_ms": float(np.mean(b_ms) + np.mean(t_ms)),
-            "default_frame_ms": build_ms_mean + ms_per_step,
             "value": n_rays / (float(np.mean(t_ms)) * 1e-3) / 1e6, "unit": "Mrays/s",
-            "refits": backend.refits - r1, "rebuilds": backend.refit_rejects - j1,
-            "warmup_frames": k, "tree_height": backend.tree_depth,
-            "note": "PRT_B200_TREELET_MODE=3: 4 distinct frames of the height field (phase 0.1*f) in "
-                    "rotation; set_tris refits the optimised topology (1 kernel + SAH check)"}
-        backend.set_tree_optimisation(int(os.environ.get("PRT_B200_TREELET_MODE", "2")), passes)
+            "default_frame_ms": (steady_set_tris_ms or 0.0) + ms_per_step,
+            "note": "PRT_B200_TREELET_MODE=2 (no temporal reuse): the same 4 frames, plain LBVH rebuilt "
+                    "by every set_tris; default_frame_ms = set_tris_ms_steady + ms_per_step of the main run"}
+        backend.set_tree_optimisation(tl_mode, tl_passes)
         backend.set_tris_dev(d_tris.data_ptr(), n_tris)
 
     cpu = None
@@ -663,7 +679,7 @@ def main():
                             % len(numa_cpus) if numa_cpus else "no NUMA binding")},
         "build_mtris_s": build["mtris_s"], "build": build,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": roofline, "cpu_baseline": cpu, "watertight": watertight, "dynamic_refit": dynamic_refit,
+        "roofline": roofline, "cpu_baseline": cpu, "watertight": watertight, "dynamic_without_reuse": dynamic_plain,
         "wall_s_timed_region": wall, "device": backend.device_name(),
     }
     if per_mask:

@@ -97,7 +97,8 @@ class CUDABackend : public InvokableBackend<CUDABackend> {
 	// Extensions beyond the reference's Backend interface (reached through the concrete type, like
 	// the member form of nearest_hits); the same knobs exist as PRT_B200_* environment variables.
 	// SAH optimisation of the BVH by treelet restructuring: 0 never, 1 inside every set_tris,
-	// 2 (default) lazily for scenes that keep being traced.  Never changes a result.
+	// 2 lazily for scenes that keep being traced, 3 (default) lazily plus temporal reuse (set_tris
+	// with the same triangle count refits the optimised topology).  Never changes a result.
 	void set_tree_optimisation(int mode, int passes = 2) {
 		need_ctx();
 		check(prt_b200_set_tree_optimisation(m_ctx, mode, passes));

@@ -134,17 +134,18 @@ int prt_b200_set_trace_opts(prt_b200 *ctx, const prt_trace_opts *opts);
  * the number of boxes visited per ray (measured: -6 % on C2, -46 % on the C3 interior).
  *   mode 0  never: set_tris leaves the radix tree as built (fastest build)
  *   mode 1  inside every set_tris
- *   mode 2  (default) lazily: once a scene has been asked for max(32 rays per triangle, 8 Mi rays)
- *           -- about when tracing the plain tree has cost what the optimisation costs -- it is
- *           optimised before the next batch is traced; a scene rebuilt every frame (config C5)
- *           never pays for it, a static one pays once
- *   mode 3  (opt-in) mode 2 plus temporal reuse for deforming meshes: rays are counted per scene
+ *   mode 2  lazily: once a scene has been asked for max(32 rays per triangle, 8 Mi rays) -- about
+ *           when tracing the plain tree has cost what the optimisation costs -- it is optimised
+ *           before the next batch is traced; a static scene pays once
+ *   mode 3  (default) mode 2 plus temporal reuse for deforming meshes: rays are counted per scene
  *           FAMILY (consecutive set_tris calls with the same triangle count), and once the family's
  *           tree has been optimised, the next set_tris of that size refits the optimised topology
  *           to the new vertices (one kernel) instead of rebuilding.  The refitted tree is kept only
  *           if its SAH cost stays within 1.25x of the cost it had when optimised; otherwise the
- *           scene is rebuilt and optimised at once.  Results never depend on it: every box is the
- *           exact union of what is below.  prt_b200_refits / prt_b200_refit_rejects count both cases.
+ *           plain LBVH is rebuilt, the family's counter starts over and its threshold doubles, so
+ *           that alternating unrelated scenes of one size costs a vanishing number of wasted
+ *           optimisations.  Results never depend on any of this: every box is the exact union of
+ *           what is below.  prt_b200_refits / prt_b200_refit_rejects count both cases.
  * passes: 1..8 (default 2).  Env PRT_B200_TREELET_MODE / PRT_B200_TREELET_PASSES.
  * prt_b200_tree_depth: height of the optimised tree (0 = the current tree is the plain radix tree);
  * prt_b200_last_optimise_ms: device time the lazy optimisation of the current scene took.

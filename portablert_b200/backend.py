@@ -159,10 +159,11 @@ class CUDABackend(Backend):
         self._need()
         self._check(lib().prt_b200_set_ray_sorting(self._h, int(mode)))
 
-    def set_tree_optimisation(self, mode: int, passes: int = 2):
+    def set_tree_optimisation(self, mode: int = 3, passes: int = 2):
         """SAH optimisation of the LBVH by treelet restructuring (Karras & Aila 2013): mode 0 never,
-        1 inside every set_tris, 2 (default) lazily once a scene has served max(32 rays per triangle,
-        8 Mi rays), 3 like 2 plus temporal reuse: frames of the same size refit the optimised topology."""
+        1 inside every set_tris, 2 lazily once a scene has served max(32 rays per triangle, 8 Mi
+        rays), 3 (default) like 2 plus temporal reuse: set_tris of the same size refits the optimised
+        topology."""
         self._need()
         self._check(lib().prt_b200_set_tree_optimisation(self._h, int(mode), int(passes)))
 

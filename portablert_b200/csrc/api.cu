@@ -278,7 +278,6 @@ static int timed_build(prt_b200 *c, const float *d_tris9, uint64_t n, float *ms)
 		return rc;
 	if (!reused) {
 		rc = prt::build_lbvh(c, d_tris9, n);
-		c->force_eager = false;
 		if (rc)
 			return rc;
 	}

@@ -842,14 +842,14 @@ static int refit_tree(prt_b200 *c, const float *d_tris9, cudaStream_t s, double 
 	return PRT_OK;
 }
 
-// Mode 3: set_tris with as many triangles as the current, optimised scene first tries the
-// previous topology (a deforming mesh keeps its connectivity and most of its shape); the refitted
-// tree is accepted if its SAH cost stays within REFIT_TOLERANCE of the cost it had when it was
-// optimised, otherwise the caller rebuilds (and, the scene family having proven itself worth it,
-// optimises right away).  *reused says which.
+// Mode 3 (the default): set_tris with as many triangles as the current, optimised scene first
+// tries the previous topology (a deforming mesh keeps its connectivity and most of its shape); the
+// refitted tree is accepted if its SAH cost stays within REFIT_TOLERANCE of the cost it had when it
+// was optimised.  Otherwise the caller rebuilds the plain LBVH, the family's ray counter starts
+// over and its threshold doubles (callers that alternate unrelated scenes of one size pay for a
+// geometrically shrinking number of wasted optimisations).  *reused says which.
 int try_reuse_topology(prt_b200 *c, const float *d_tris9, uint64_t n, cudaStream_t s, bool *reused) {
 	*reused = false;
-	c->force_eager = false;
 	if (c->optimise_mode != 3 || !c->topology_valid || !c->tree_optimised || n != c->n_tris ||
 	    c->recs_vertex_form != (c->watertight != 0))
 		return PRT_OK;
@@ -861,10 +861,12 @@ int try_reuse_topology(prt_b200 *c, const float *d_tris9, uint64_t n, cudaStream
 			return rc;
 		c->refits++;
 		c->last_sah = sah;
+		c->lazy_backoff = 1;
 		*reused = true;
 	} else {
 		c->refit_rejects++;
-		c->force_eager = true;
+		c->rays_since_build = 0;
+		c->lazy_backoff = std::min<uint64_t>(64, c->lazy_backoff * 2);
 	}
 	return PRT_OK;
 }
@@ -924,7 +926,8 @@ int optimise_tree(prt_b200 *c, cudaStream_t s) {
 int maybe_optimise_tree(prt_b200 *c, uint64_t n_rays) {
 	c->rays_since_build += n_rays;
 	if (c->optimise_mode < 2 || c->tree_optimised || c->n_tris < (uint64_t)TREELET_N ||
-	    c->rays_since_build < std::max<uint64_t>(LAZY_RAYS_PER_TRI * c->n_tris, LAZY_MIN_RAYS))
+	    c->rays_since_build <
+	        c->lazy_backoff * std::max<uint64_t>(LAZY_RAYS_PER_TRI * c->n_tris, LAZY_MIN_RAYS))
 		return PRT_OK;
 	cudaStream_t s = c->stream;
 	PRT_CUDA(c, cudaEventRecord(c->ev0, s));
@@ -966,8 +969,10 @@ static int morton_bits_for(uint64_t n) {
 int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 	cudaStream_t s = c->stream;
 	// (mode 3 counts the rays of a scene FAMILY: frames of the same size keep the counter)
-	if (!(c->optimise_mode == 3 && n == c->n_tris))
+	if (!(c->optimise_mode == 3 && n == c->n_tris)) {
 		c->rays_since_build = 0;
+		c->lazy_backoff = 1;
+	}
 	c->n_tris = n;
 	c->n_nodes = n == 0 ? 0 : (n == 1 ? 1 : n - 1);
 	c->wide_built = false;
@@ -1024,7 +1029,7 @@ int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 		                              c->bound.as<int>(), c->root_info.as<RootInfo>(), vf);
 		c->launches += 1;
 	}
-	if (c->optimise_mode == 1 || c->force_eager) // inside every set_tris / a rejected refit
+	if (c->optimise_mode == 1) // inside every set_tris
 		if (int rc = optimise_tree(c, s))
 			return rc;
 	c->wide_built = !vf && (c->wide_mode == 1 || (c->wide_mode == 2 && n >= (1ull << 20)));

@@ -91,10 +91,11 @@ struct prt_b200 {
 	prt::DevBuf keys[2], vals[2], sort_scratch, bounds, leaf_box, bound, root_info;
 	// opt-in treelet SAH optimisation (build.cu 5b): parent links, arrival flags, leaf counts, heights
 	prt::DevBuf tl_parent, tl_leaf_parent, tl_flag, tl_count, tl_depth, tl_backup, tl_sah;
-	int optimise_mode = 2;   // env PRT_B200_TREELET_MODE: 0 never, 1 inside set_tris, 2 lazily (default), 3 lazily + temporal reuse
+	int optimise_mode = 3;   // env PRT_B200_TREELET_MODE: 0 never, 1 inside set_tris, 2 lazily, 3 lazily + temporal reuse (default)
 	int optimise_passes = 2; // env PRT_B200_TREELET_PASSES
 	bool tree_optimised = false;
-	bool topology_valid = false, force_eager = false; // mode 3: parent links match the nodes / rebuild optimises at once
+	bool topology_valid = false;                      // mode 3: parent links match the nodes
+	uint64_t lazy_backoff = 1;                        // mode 3: threshold multiplier, doubled by every rejected refit
 	double sah_ref = 0.0, last_sah = 0.0;             // mode 3: SAH cost when optimised / after the last refit
 	uint64_t refits = 0, refit_rejects = 0;
 	uint64_t rays_since_build = 0, strict_fallbacks = 0;

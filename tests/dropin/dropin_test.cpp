@@ -213,7 +213,7 @@ int main() {
 		            rays.size());
 	}
 	cb->set_watertight(false);
-	cb->set_tree_optimisation(2);
+	cb->set_tree_optimisation(3);
 	cuda->set_tris(tris);
 	compare<ALL_TAGS>("full, defaults restored", nearest_hits(rays), ref, st);
 

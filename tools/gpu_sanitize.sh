@@ -38,7 +38,7 @@ for tris in (scenes.KAT_TRI, scenes.blob(24, 24), scenes.interior(4000), np.repe
     b.nearest_hits(rays[:5000], "valid")
     b.set_triangle_test(0)
     b.set_wide_nodes(2)
-    b.set_tree_optimisation(2, 2)
+    b.set_tree_optimisation(3, 2)
 print("sanitizer workload ok")
 PY
 for tool in memcheck racecheck synccheck; do
