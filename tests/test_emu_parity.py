@@ -407,3 +407,36 @@ def test_lane_parallel_split_search_equals_the_sequential_recurrence(emu):
         tables.append(t)
     for t in tables:
         assert emu.check_split_search(t) == 0
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_random_scenes_default_and_watertight(seed, oracle, emu):
+    """random triangle soups of mixed sizes, random and axis-parallel rays: the kernel source on the
+    plain and on the optimised tree == oracle (default mode) and == the numpy restatement
+    (watertight mode, which also covers the NaN planes of axis-parallel rays)"""
+    import woop_check
+    g = np.random.default_rng(100 + seed)
+    n = int(g.integers(40, 500))
+    c = g.random((n, 1, 3), dtype=np.float32) * 2 - 1
+    size = (10.0 ** g.uniform(-2.5, -0.2, (n, 1, 1))).astype(np.float32)
+    tris = (c + (g.random((n, 3, 3), dtype=np.float32) - 0.5) * size).reshape(-1, 9).astype(np.float32)
+    rays = scenes.incoherent_rays(1200, [-1.2] * 3, [1.2] * 3, seed)
+    axis = rays[:300].copy()  # axis-parallel and planar rays starting on a grid of round numbers
+    axis[:, :3] = np.round(axis[:, :3] * 4) / 4
+    axis[np.arange(300), 3 + g.integers(0, 3, 300)] = 0
+    axis[::3, 3 + g.integers(0, 3)] = 0
+    oracle.build(tris)
+    emu.build(tris, 10)
+    for stage in range(2):
+        got = emu.trace(rays)
+        rep = parity.compare(oracle.trace(rays), got, tris, rays, oracle)
+        parity.assert_parity(rep)
+        assert rep["t_equal"], rep
+        emu.treelet(2)
+    emu.build(tris, 10, watertight=True)
+    emu.treelet(1)
+    allrays = np.concatenate([rays[:400], axis])
+    want = woop_check.brute(tris, allrays)
+    got = emu.trace(allrays, watertight=True)
+    for k in ("valid", "t", "pid", "u", "v"):
+        assert np.array_equal(got[k], want[k], equal_nan=True), (seed, k)
