@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PRT_B200_ABI_VERSION 2 /* 2: tree optimisation, triangle test */
+#define PRT_B200_ABI_VERSION 3 /* 2: tree optimisation, triangle test; 3: multi-GPU contexts */
 
 enum {
 	PRT_OK = 0,
@@ -71,8 +71,30 @@ typedef struct prt_b200 prt_b200; /* opaque: owns streams, scratch, the BVH, sta
 int prt_b200_device_count(void);
 
 /* Backend::init (backend.hpp:21), called by select_backend (src/backend.cpp:50-56), possibly more
- * than once.  device < 0 selects env PRT_B200_DEVICE or the first CC 10.x device. */
+ * than once.  device >= 0: a single-GPU context on that device.  device < 0: what the environment
+ * asks for -- PRT_B200_GPUS devices (default 1) starting at PRT_B200_DEVICE (default: the first
+ * CC 10.x device) -- so that a program written against the reference API spreads over several
+ * GPUs without a source change. */
 int prt_b200_create(prt_b200 **out, int device);
+
+/* Multi-GPU context: n_gpus CC 10.x devices driven from this one process (n_gpus <= 0: env
+ * PRT_B200_GPUS, default 1).  The reference API has one scene and one ray batch per call
+ * (backend.hpp:19,75-83) and rays are independent, so the scene replicates and the batch shards:
+ *   set_tris      the triangles go to the first device once and are broadcast to the others over
+ *                 NVLink (one grouped ncclBroadcast on single-process communicators; libnccl is
+ *                 resolved at run time, cudaMemcpyPeerAsync where it cannot be loaded or
+ *                 PRT_B200_BCAST=p2p); every device runs the same deterministic build, so all
+ *                 replicas of the BVH are bit-identical
+ *   nearest_hits  device i traces the contiguous slice [i*n/G, (i+1)*n/G) of the caller's host
+ *                 batch through its own copy pipeline (one host thread per device) and writes its
+ *                 records at the slice's offset of the caller's array: hits arrive in ray order,
+ *                 there is no gather step and no collective on the data path
+ * Results are byte-for-byte those of a single-GPU context.  The device-resident entry points
+ * (prt_b200_set_tris_dev takes a pointer on the first device and broadcasts from there;
+ * prt_b200_trace_dev*, prt_b200_download_*) act on the first device. */
+int prt_b200_create_multi(prt_b200 **out, int n_gpus);
+int prt_b200_num_devices(const prt_b200 *ctx);
+const char *prt_b200_broadcast_path(const prt_b200 *ctx); /* "nccl" / "p2p" / "" (nothing broadcast yet) */
 
 /* Backend::shutdown (backend.hpp:22); NULL-safe, frees all device and pinned memory. */
 void prt_b200_destroy(prt_b200 *ctx);
@@ -102,6 +124,13 @@ int prt_b200_set_tris_dev(prt_b200 *ctx, const float *d_tris9, uint64_t n_tris, 
  * reference leaves indeterminate on a miss are written as u = v = 0, primitive_id = 0xFFFFFFFF. */
 int prt_b200_nearest_hits(prt_b200 *ctx, const float *rays6, uint64_t n_rays, uint32_t tag_mask,
                           const prt_hit_layout *layout, void *hits_out);
+
+/* bytes the last prt_b200_nearest_hits moved host->device and device->host (all devices).  Results
+ * for pageable caller memory cross PCIe tightly packed (requested fields only) and are scattered
+ * into the caller's records by the staging threads; pinned caller memory receives the records by
+ * DMA as they are. */
+uint64_t prt_b200_last_h2d_bytes(const prt_b200 *ctx);
+uint64_t prt_b200_last_d2h_bytes(const prt_b200 *ctx);
 
 /* Page-locked host memory.  prt_b200_set_tris / prt_b200_nearest_hits detect pinned (or
  * cudaHostRegister'ed) buffers and DMA from/to them directly; pageable memory (e.g. a plain

@@ -34,6 +34,11 @@ SYMBOLS = {
     "prt_b200_abi_version": (C.c_int, []),
     "prt_b200_device_count": (C.c_int, []),
     "prt_b200_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "prt_b200_create_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "prt_b200_num_devices": (C.c_int, [C.c_void_p]),
+    "prt_b200_broadcast_path": (C.c_char_p, [C.c_void_p]),
+    "prt_b200_last_h2d_bytes": (C.c_uint64, [C.c_void_p]),
+    "prt_b200_last_d2h_bytes": (C.c_uint64, [C.c_void_p]),
     "prt_b200_destroy": (None, [C.c_void_p]),
     "prt_b200_device_name": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "prt_b200_set_tris": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),

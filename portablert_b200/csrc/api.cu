@@ -8,11 +8,13 @@
 #include <cstdlib>
 #include <condition_variable>
 #include <cstring>
+#include <dlfcn.h>
 #include <mutex>
 #include <thread>
 #include <vector>
 
 #include "prt_ctx.h"
+#include "prt_hostpool.h"
 
 using prt::fail;
 
@@ -51,6 +53,72 @@ struct Progress {
 
 static thread_local std::string g_create_err;
 
+namespace prt {
+// libnccl resolved at run time (dlopen): the library is only needed by multi-GPU contexts, and a
+// process that already carries an NCCL (e.g. one that imported torch) shares that copy.  Only the
+// five entry points of the triangle broadcast are used; ncclComm_t is an opaque pointer,
+// ncclResult_t / ncclDataType_t are ints (ncclChar == 0).
+struct NcclApi {
+	void *handle = nullptr;
+	int (*CommInitAll)(void **, int, const int *) = nullptr;
+	int (*CommDestroy)(void *) = nullptr;
+	int (*GroupStart)() = nullptr;
+	int (*GroupEnd)() = nullptr;
+	int (*Broadcast)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+	const char *(*GetErrorString)(int) = nullptr;
+	bool load() {
+		for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+			handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+			if (handle)
+				break;
+		}
+		if (!handle)
+			return false;
+		CommInitAll = reinterpret_cast<decltype(CommInitAll)>(dlsym(handle, "ncclCommInitAll"));
+		CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(handle, "ncclCommDestroy"));
+		GroupStart = reinterpret_cast<decltype(GroupStart)>(dlsym(handle, "ncclGroupStart"));
+		GroupEnd = reinterpret_cast<decltype(GroupEnd)>(dlsym(handle, "ncclGroupEnd"));
+		Broadcast = reinterpret_cast<decltype(Broadcast)>(dlsym(handle, "ncclBroadcast"));
+		GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(handle, "ncclGetErrorString"));
+		return CommInitAll && CommDestroy && GroupStart && GroupEnd && Broadcast;
+	}
+};
+} // namespace prt
+
+// every device of a (possibly multi-GPU) context: [0] = the context itself
+static std::vector<prt_b200 *> all_devices(prt_b200 *c) {
+	std::vector<prt_b200 *> v{c};
+	v.insert(v.end(), c->peers.begin(), c->peers.end());
+	return v;
+}
+
+// fn(sub-context, index) on every device concurrently (one host thread per further device, the
+// caller's thread drives device 0); returns the first error, whose message is copied to the owner
+template <class F> static int on_all_devices(prt_b200 *c, F fn) {
+	if (c->peers.empty())
+		return fn(c, 0);
+	const auto devs = all_devices(c);
+	std::vector<int> rc(devs.size(), PRT_OK);
+	std::vector<std::thread> th;
+	for (size_t i = 1; i < devs.size(); ++i)
+		th.emplace_back([&, i] {
+			cudaSetDevice(devs[i]->device);
+			rc[i] = fn(devs[i], (int)i);
+		});
+	cudaSetDevice(c->device);
+	rc[0] = fn(c, 0);
+	for (auto &t : th)
+		t.join();
+	cudaSetDevice(c->device);
+	for (size_t i = 0; i < devs.size(); ++i)
+		if (rc[i] != PRT_OK) {
+			if (i)
+				c->err = "device " + std::to_string(devs[i]->device) + ": " + devs[i]->err;
+			return rc[i];
+		}
+	return PRT_OK;
+}
+
 extern "C" {
 
 int prt_b200_abi_version(void) { return PRT_B200_ABI_VERSION; }
@@ -75,37 +143,8 @@ const char *prt_b200_last_error(const prt_b200 *c) {
 	return c ? c->err.c_str() : g_create_err.c_str();
 }
 
-int prt_b200_create(prt_b200 **out, int device) {
-	if (!out) {
-		g_create_err = "create: out == NULL";
-		return PRT_E_ARG;
-	}
-	*out = nullptr;
-	int n = 0;
-	if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
-		cudaGetLastError();
-		g_create_err = "no CUDA device visible (this backend has no CPU fallback)";
-		return PRT_E_NO_DEVICE;
-	}
-	if (device < 0) {
-		if (const char *e = std::getenv("PRT_B200_DEVICE"))
-			device = std::atoi(e);
-	}
-	if (device < 0) {
-		for (int d = 0; d < n && device < 0; ++d) {
-			int major = 0;
-			cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d);
-			if (major == 10)
-				device = d;
-		}
-	}
-	int major = 0;
-	if (device < 0 || device >= n ||
-	    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess ||
-	    major != 10) {
-		g_create_err = "no compute-capability-10.x (sm_100a) device: kernels are built for B200 only";
-		return PRT_E_NO_DEVICE;
-	}
+// One single-device context (the whole context of a 1-GPU backend, a sub-context otherwise).
+static int create_one(prt_b200 **out, int device) {
 	prt_b200 *c = new prt_b200();
 	c->device = device;
 	cudaError_t e = cudaSetDevice(device);
@@ -139,6 +178,7 @@ int prt_b200_create(prt_b200 **out, int device) {
 		return PRT_E_CUDA;
 	}
 	c->sm_count = prop.multiProcessorCount;
+	c->l2_bytes = (uint64_t)prop.l2CacheSize;
 	if (const char *e = std::getenv("PRT_B200_FAST_BOXES"))
 		c->fast_boxes = std::atoi(e) != 0;
 	if (const char *e = std::getenv("PRT_B200_TREELET_MODE"))
@@ -155,7 +195,8 @@ int prt_b200_create(prt_b200 **out, int device) {
 		c->sort_rays = std::max(0, std::min(2, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_RAYKEY")) {
 		int ob = 0, db = 0;
-		if (std::sscanf(e, "%d,%d", &ob, &db) == 2 && ob >= 1 && ob <= 10 && db >= 0 && db <= 10) {
+		if (std::sscanf(e, "%d,%d", &ob, &db) == 2 && ob >= 1 && ob <= 10 && db >= 0 && db <= 10 &&
+		    3 * (ob + db) <= 32) {
 			c->ray_key_ob = ob;
 			c->ray_key_db = db;
 		}
@@ -166,43 +207,154 @@ int prt_b200_create(prt_b200 **out, int device) {
 		c->chunk_log2 = std::max(10, std::min(19, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_REFILL"))
 		c->refill = std::max(0, std::min(32, std::atoi(e)));
+	if (const char *e = std::getenv("PRT_B200_LEAF_VOTES"))
+		c->leaf_votes = std::max(1, std::min(32, std::atoi(e)));
+	if (const char *e = std::getenv("PRT_B200_PREFETCH"))
+		c->prefetch = std::max(0, std::min(2, std::atoi(e)));
+	if (const char *e = std::getenv("PRT_B200_COPY_THREADS"))
+		c->copy_threads = std::max(1, std::min(32, std::atoi(e)));
+	if (const char *e = std::getenv("PRT_B200_BCAST"))
+		c->bcast_mode = std::strcmp(e, "p2p") == 0 ? 1 : 0;
+	if (const char *e = std::getenv("PRT_B200_PACKED_D2H"))
+		c->packed_d2h = std::atoi(e) != 0;
 	c->name = prop.name;
 	*out = c;
 	return PRT_OK;
 }
 
+// the CC 10.x devices in enumeration order
+static std::vector<int> cc10_devices() {
+	std::vector<int> v;
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return v;
+	}
+	for (int d = 0; d < n; ++d) {
+		int major = 0;
+		if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess &&
+		    major == 10)
+			v.push_back(d);
+	}
+	return v;
+}
+
+int prt_b200_create_multi(prt_b200 **out, int n_gpus) {
+	if (!out) {
+		g_create_err = "create: out == NULL";
+		return PRT_E_ARG;
+	}
+	*out = nullptr;
+	const std::vector<int> devs = cc10_devices();
+	if (devs.empty()) {
+		g_create_err = "no compute-capability-10.x (sm_100a) device visible: kernels are built for "
+		               "B200 only and this backend has no CPU fallback";
+		return PRT_E_NO_DEVICE;
+	}
+	if (n_gpus <= 0) {
+		const char *e = std::getenv("PRT_B200_GPUS");
+		n_gpus = e ? std::atoi(e) : 1;
+		if (n_gpus <= 0)
+			n_gpus = 1;
+	}
+	if ((size_t)n_gpus > devs.size()) {
+		g_create_err = "create: " + std::to_string(n_gpus) + " GPUs requested, " +
+		               std::to_string(devs.size()) + " compute-capability-10.x devices visible";
+		return PRT_E_NO_DEVICE;
+	}
+	// the first device may be chosen with PRT_B200_DEVICE (the others follow in enumeration order)
+	size_t first = 0;
+	if (const char *e = std::getenv("PRT_B200_DEVICE")) {
+		const int want = std::atoi(e);
+		for (size_t k = 0; k < devs.size(); ++k)
+			if (devs[k] == want)
+				first = k;
+	}
+	prt_b200 *c = nullptr;
+	if (int rc = create_one(&c, devs[first]))
+		return rc;
+	for (int k = 1; k < n_gpus; ++k) {
+		prt_b200 *p = nullptr;
+		if (int rc = create_one(&p, devs[(first + k) % devs.size()])) {
+			prt_b200_destroy(c);
+			return rc;
+		}
+		c->peers.push_back(p);
+	}
+	if (n_gpus > 1) {
+		// peer access lets the triangle broadcast (NCCL or cudaMemcpyPeerAsync) take NVLink
+		const auto all = all_devices(c);
+		for (auto *a : all) {
+			cudaSetDevice(a->device);
+			for (auto *b : all)
+				if (a != b) {
+					int can = 0;
+					cudaDeviceCanAccessPeer(&can, a->device, b->device);
+					if (can && cudaDeviceEnablePeerAccess(b->device, 0) != cudaSuccess)
+						cudaGetLastError(); // already enabled
+				}
+		}
+		c->name += " x" + std::to_string(n_gpus);
+	}
+	cudaSetDevice(c->device);
+	*out = c;
+	return PRT_OK;
+}
+
+int prt_b200_create(prt_b200 **out, int device) {
+	if (!out) {
+		g_create_err = "create: out == NULL";
+		return PRT_E_ARG;
+	}
+	*out = nullptr;
+	if (device < 0) // env PRT_B200_DEVICE / PRT_B200_GPUS: a drop-in user needs no source change
+		return prt_b200_create_multi(out, 0);
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+		cudaGetLastError();
+		g_create_err = "no CUDA device visible (this backend has no CPU fallback)";
+		return PRT_E_NO_DEVICE;
+	}
+	int major = 0;
+	if (device >= n ||
+	    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess ||
+	    major != 10) {
+		g_create_err = "no compute-capability-10.x (sm_100a) device: kernels are built for B200 only";
+		return PRT_E_NO_DEVICE;
+	}
+	return create_one(out, device);
+}
+
+int prt_b200_num_devices(const prt_b200 *c) { return c ? 1 + (int)c->peers.size() : 0; }
+
 void prt_b200_destroy(prt_b200 *c) {
 	if (!c)
 		return;
+	for (prt_b200 *p : c->peers)
+		prt_b200_destroy(p);
+	c->peers.clear();
+	if (c->nccl) {
+		for (void *comm : c->nccl_comms)
+			if (comm)
+				c->nccl->CommDestroy(comm);
+		delete c->nccl; // (the library handle stays loaded: other users in the process may share it)
+		c->nccl = nullptr;
+	}
 	if (c->device >= 0)
 		cudaSetDevice(c->device);
+	for (int k = 0; k < 3; ++k)
+		if (c->pipe_stream[k])
+			cudaStreamSynchronize(c->pipe_stream[k]);
 	if (c->stream)
 		cudaStreamSynchronize(c->stream);
-	prt::DevBuf *bufs[] = {&c->tris_raw, &c->nodes,    &c->trirecs,     &c->nodes4,     &c->keys[0],     &c->keys[1],
-	                       &c->vals[0],  &c->vals[1],  &c->sort_scratch, &c->bounds,
-	                       &c->leaf_box, &c->bound,    &c->root_info,
-	                       &c->counter};
-	for (auto *b : bufs)
-		b->release();
-	c->probe_ticket.release();
+	delete c->pool_in;
+	delete c->pool_out;
 	if (c->probe_host)
 		cudaFreeHost(c->probe_host);
-	for (auto &r : c->rs) {
-		r.keys[0].release();
-		r.keys[1].release();
-		r.vals[0].release();
-		r.vals[1].release();
-		r.scratch.release();
-	}
-	for (int k = 0; k < prt_b200::PIPE; ++k) {
-		c->rays_dev[k].release();
-		c->hits_dev[k].release();
-		c->rays_pin[k].release();
-		c->hits_pin[k].release();
+	for (int k = 0; k < prt_b200::PIPE; ++k)
 		for (int j = 0; j < 3; ++j)
 			if (c->ev_pipe[k][j])
 				cudaEventDestroy(c->ev_pipe[k][j]);
-	}
 	for (int k = 0; k < 3; ++k)
 		if (c->pipe_stream[k])
 			cudaStreamDestroy(c->pipe_stream[k]);
@@ -212,7 +364,7 @@ void prt_b200_destroy(prt_b200 *c) {
 		cudaEventDestroy(c->ev1);
 	if (c->stream)
 		cudaStreamDestroy(c->stream);
-	delete c;
+	delete c; // DevBuf / PinnedBuf members release their memory (prt_ctx.h)
 }
 
 int prt_b200_device_name(const prt_b200 *c, char *buf, size_t cap) {
@@ -226,15 +378,18 @@ int prt_b200_device_name(const prt_b200 *c, char *buf, size_t cap) {
 int prt_b200_set_wide_nodes(prt_b200 *c, int mode) {
 	if (!c || mode < 0 || mode > 2)
 		return fail(c, PRT_E_ARG, "set_wide_nodes: mode must be 0, 1 or 2");
-	c->wide_mode = mode;
+	for (prt_b200 *d : all_devices(c))
+		d->wide_mode = mode;
 	return PRT_OK;
 }
 
 int prt_b200_set_tree_optimisation(prt_b200 *c, int mode, int passes) {
 	if (!c || mode < 0 || mode > 3 || passes < 1 || passes > 8)
 		return fail(c, PRT_E_ARG, "set_tree_optimisation: mode must be 0..3 and passes 1..8");
-	c->optimise_mode = mode;
-	c->optimise_passes = passes;
+	for (prt_b200 *d : all_devices(c)) {
+		d->optimise_mode = mode;
+		d->optimise_passes = passes;
+	}
 	return PRT_OK;
 }
 int32_t prt_b200_tree_depth(const prt_b200 *c) { return c ? c->tree_depth : 0; }
@@ -246,7 +401,8 @@ uint64_t prt_b200_refit_rejects(const prt_b200 *c) { return c ? c->refit_rejects
 int prt_b200_set_triangle_test(prt_b200 *c, int mode) {
 	if (!c || mode < 0 || mode > 1)
 		return fail(c, PRT_E_ARG, "set_triangle_test: mode must be 0 or 1");
-	c->watertight = mode;
+	for (prt_b200 *d : all_devices(c))
+		d->watertight = mode;
 	return PRT_OK;
 }
 int prt_b200_triangle_test(const prt_b200 *c) { return c && c->recs_vertex_form ? 1 : 0; }
@@ -254,7 +410,8 @@ int prt_b200_triangle_test(const prt_b200 *c) { return c && c->recs_vertex_form 
 int prt_b200_set_ray_sorting(prt_b200 *c, int mode) {
 	if (!c || mode < 0 || mode > 2)
 		return fail(c, PRT_E_ARG, "set_ray_sorting: mode must be 0, 1 or 2");
-	c->sort_rays = mode;
+	for (prt_b200 *d : all_devices(c))
+		d->sort_rays = mode;
 	return PRT_OK;
 }
 uint64_t prt_b200_sorted_batches(const prt_b200 *c) { return c ? c->sorted_batches : 0; }
@@ -262,14 +419,26 @@ uint64_t prt_b200_sorted_batches(const prt_b200 *c) { return c ? c->sorted_batch
 int prt_b200_set_trace_opts(prt_b200 *c, const prt_trace_opts *o) {
 	if (!c)
 		return PRT_E_ARG;
-	if (o)
-		c->opts = *o;
-	else
-		c->opts = prt_trace_opts{1, 1e-4f, 64.0f};
+	for (prt_b200 *d : all_devices(c))
+		d->opts = o ? *o : prt_trace_opts{1, 1e-4f, 64.0f};
 	return PRT_OK;
 }
 
-static int timed_build(prt_b200 *c, const float *d_tris9, uint64_t n, float *ms) {
+// A failed build must not leave a half-committed scene behind (buffers freed or undersized but
+// n_tris > 0): fall back to the empty scene, on which every ray misses.
+static void reset_scene(prt_b200 *c) {
+	c->n_tris = 0;
+	c->n_nodes = 0;
+	c->root = 0;
+	c->wide_built = false;
+	c->tree_optimised = false;
+	c->topology_valid = false;
+	c->tree_depth = 0;
+	for (int a = 0; a < 3; ++a)
+		c->scene_lo[a] = c->scene_hi[a] = c->scene_absmax[a] = 0.f;
+}
+
+static int timed_build_raw(prt_b200 *c, const float *d_tris9, uint64_t n) {
 	PRT_CUDA(c, cudaSetDevice(c->device));
 	PRT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
 	bool reused = false;
@@ -298,6 +467,104 @@ static int timed_build(prt_b200 *c, const float *d_tris9, uint64_t n, float *ms)
 		c->scene_hi[a] = c->n_nodes ? ri.hi[a] : 0.f;
 		c->scene_absmax[a] = std::max(std::fabs(c->scene_lo[a]), std::fabs(c->scene_hi[a]));
 	}
+	return PRT_OK;
+}
+
+static int timed_build(prt_b200 *c, const float *d_tris9, uint64_t n, float *ms) {
+	const int rc = timed_build_raw(c, d_tris9, n);
+	if (rc) {
+		const std::string keep = c->err;
+		cudaStreamSynchronize(c->stream);
+		if (cudaGetLastError() != cudaSuccess) { /* non-sticky errors are cleared; sticky ones stay */
+		}
+		reset_scene(c);
+		c->err = keep;
+		return rc;
+	}
+	if (ms)
+		*ms = c->last_build_ms;
+	return PRT_OK;
+}
+
+// Multi-GPU: the triangles that device 0 holds at `src` reach every further device's tris_raw over
+// NVLink -- one grouped ncclBroadcast on per-device communicators (ncclCommInitAll, single
+// process), or cudaMemcpyPeerAsync where libnccl cannot be loaded (PRT_B200_BCAST=p2p forces it).
+static int broadcast_tris(prt_b200 *c, const float *src, uint64_t n) {
+	const auto devs = all_devices(c);
+	const size_t bytes = (size_t)n * 36;
+	for (size_t i = 1; i < devs.size(); ++i) {
+		PRT_CUDA(c, cudaSetDevice(devs[i]->device));
+		PRT_CUDA(c, devs[i]->tris_raw.reserve(bytes));
+	}
+	PRT_CUDA(c, cudaSetDevice(c->device));
+	if (bytes == 0)
+		return PRT_OK;
+	if (c->bcast_mode == 0 && !c->nccl) {
+		auto *api = new prt::NcclApi();
+		bool ok = api->load();
+		if (ok) {
+			std::vector<int> ids;
+			for (auto *d : devs)
+				ids.push_back(d->device);
+			c->nccl_comms.assign(devs.size(), nullptr);
+			ok = api->CommInitAll(c->nccl_comms.data(), (int)devs.size(), ids.data()) == 0;
+			if (!ok)
+				c->nccl_comms.clear();
+			cudaSetDevice(c->device);
+		}
+		if (ok)
+			c->nccl = api;
+		else {
+			delete api;
+			c->bcast_mode = 1;
+		}
+	}
+	if (c->nccl) {
+		int rc = c->nccl->GroupStart();
+		for (size_t i = 0; i < devs.size() && rc == 0; ++i)
+			rc = c->nccl->Broadcast(src, i == 0 ? (void *)src : devs[i]->tris_raw.p, bytes, 0 /*ncclChar*/,
+			                        0, c->nccl_comms[i], devs[i]->stream);
+		const int rc2 = c->nccl->GroupEnd();
+		if (rc || rc2) {
+			const int bad = rc ? rc : rc2;
+			return fail(c, PRT_E_CUDA, c->nccl->GetErrorString ? c->nccl->GetErrorString(bad)
+			                                                   : "ncclBroadcast failed");
+		}
+		c->bcast_used = "nccl";
+	} else {
+		// the source must be complete before the peers' streams read it
+		PRT_CUDA(c, cudaStreamSynchronize(c->stream));
+		for (size_t i = 1; i < devs.size(); ++i)
+			PRT_CUDA(c, cudaMemcpyPeerAsync(devs[i]->tris_raw.p, devs[i]->device, src, c->device, bytes,
+			                                devs[i]->stream));
+		c->bcast_used = "p2p";
+	}
+	for (auto *d : devs) {
+		PRT_CUDA(c, cudaSetDevice(d->device));
+		PRT_CUDA(c, cudaStreamSynchronize(d->stream));
+	}
+	PRT_CUDA(c, cudaSetDevice(c->device));
+	return PRT_OK;
+}
+
+const char *prt_b200_broadcast_path(const prt_b200 *c) { return c ? c->bcast_used.c_str() : ""; }
+
+// build on every device from its own copy of the triangles (deterministic: identical BVHs)
+static int build_everywhere(prt_b200 *c, const float *d_tris9_dev0, uint64_t n, float *ms) {
+	if (c->peers.empty())
+		return timed_build(c, d_tris9_dev0, n, ms);
+	if (int rc = broadcast_tris(c, d_tris9_dev0, n))
+		return rc;
+	const int rc = on_all_devices(c, [&](prt_b200 *d, int i) {
+		return timed_build(d, i == 0 ? d_tris9_dev0 : d->tris_raw.as<float>(), n, nullptr);
+	});
+	if (rc) { // all devices or none
+		for (prt_b200 *d : all_devices(c))
+			reset_scene(d);
+		return rc;
+	}
+	for (prt_b200 *d : c->peers)
+		c->last_build_ms = std::max(c->last_build_ms, d->last_build_ms);
 	if (ms)
 		*ms = c->last_build_ms;
 	return PRT_OK;
@@ -306,7 +573,7 @@ static int timed_build(prt_b200 *c, const float *d_tris9, uint64_t n, float *ms)
 int prt_b200_set_tris_dev(prt_b200 *c, const float *d_tris9, uint64_t n, float *build_ms) {
 	if (!c || (n && !d_tris9))
 		return fail(c, PRT_E_ARG, "set_tris_dev: NULL argument");
-	return timed_build(c, d_tris9, n, build_ms);
+	return build_everywhere(c, d_tris9, n, build_ms);
 }
 
 int prt_b200_set_tris(prt_b200 *c, const float *tris9, uint64_t n) {
@@ -317,7 +584,7 @@ int prt_b200_set_tris(prt_b200 *c, const float *tris9, uint64_t n) {
 		PRT_CUDA(c, c->tris_raw.reserve(n * 36));
 		PRT_CUDA(c, cudaMemcpyAsync(c->tris_raw.p, tris9, n * 36, cudaMemcpyHostToDevice, c->stream));
 	}
-	return timed_build(c, c->tris_raw.as<float>(), n, nullptr);
+	return build_everywhere(c, c->tris_raw.as<float>(), n, nullptr);
 }
 
 static int check_layout(prt_b200 *c, uint32_t mask, const prt_hit_layout *l) {
@@ -348,12 +615,24 @@ static int timed_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t m
                        const prt::TraceOut &out, uint32_t *d_counts, float *ms) {
 	PRT_CUDA(c, cudaSetDevice(c->device));
 	PRT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-	int rc = prt::launch_trace(c, d_rays6, n, mask, out, d_counts, c->stream);
+	int rc = prt::launch_trace(c, d_rays6, n, mask, out, d_counts, c->stream, -1, prt::EXOTIC_DEFERRED);
 	if (rc)
 		return rc;
 	PRT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
 	PRT_CUDA(c, cudaStreamSynchronize(c->stream));
 	PRT_CUDA(c, cudaEventElapsedTime(&c->last_trace_ms, c->ev0, c->ev1));
+	// rays the fast kernel set aside (non-finite / overflowing components): exact kernel, timed too
+	bool ran = false;
+	PRT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+	if ((rc = prt::finish_exotic(c, c->stream, &ran)))
+		return rc;
+	if (ran) {
+		float more = 0.f;
+		PRT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+		PRT_CUDA(c, cudaStreamSynchronize(c->stream));
+		PRT_CUDA(c, cudaEventElapsedTime(&more, c->ev0, c->ev1));
+		c->last_trace_ms += more;
+	}
 	if (ms)
 		*ms = c->last_trace_ms;
 	return PRT_OK;
@@ -399,121 +678,178 @@ int prt_b200_trace_count_dev(prt_b200 *c, const float *d_rays6, uint64_t n, uint
 	return timed_trace(c, d_rays6, n, PRT_TAG_ALL, out, d_counts, nullptr);
 }
 
+} // extern "C"
+
 // ---- host-pointer entry point -------------------------------------------------------------------
-static bool is_pinned(const void *p) {
-	cudaPointerAttributes a{};
-	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-		cudaGetLastError();
+// true iff the WHOLE range is page-locked host memory (a buffer of which only a part was
+// registered must be staged like pageable memory, not DMA'd)
+static bool is_pinned(const void *p, size_t bytes) {
+	auto host = [](const void *q) {
+		cudaPointerAttributes a{};
+		if (cudaPointerGetAttributes(&a, q) != cudaSuccess) {
+			cudaGetLastError();
+			return false;
+		}
+		return a.type == cudaMemoryTypeHost;
+	};
+	if (!host(p))
 		return false;
-	}
-	return a.type == cudaMemoryTypeHost;
+	return bytes == 0 || host(static_cast<const char *>(p) + bytes - 1);
 }
 
-// memcpy split over a few host threads: staging 50-100 MB through one core would cost more than
-// the PCIe transfer and the traversal together
-static void par_memcpy(void *dst, const void *src, size_t bytes) {
-	const size_t MIN_PER_THREAD = 2u << 20;
-	static const int max_threads = [] {
-		const char *e = std::getenv("PRT_B200_COPY_THREADS");
-		return e ? std::max(1, std::min(32, std::atoi(e))) : 8;
-	}();
-	unsigned hw = std::thread::hardware_concurrency();
-	size_t nt = std::min<size_t>(std::min<size_t>(hw ? hw : 1, (size_t)max_threads),
-	                             bytes / MIN_PER_THREAD);
-	if (nt <= 1) {
-		std::memcpy(dst, src, bytes);
-		return;
+static prt::HostPool *staging_pool(prt_b200 *c, prt::HostPool *&slot, int n_devices) {
+	if (!slot) {
+		int t = c->copy_threads;
+		if (t <= 0) { // two pools per device (in, out): leave the box's cores to all of them
+			const unsigned hw = std::thread::hardware_concurrency();
+			t = (int)std::max(1u, std::min(8u, (hw ? hw : 4u) / (2u * (unsigned)std::max(1, n_devices))));
+		}
+		slot = new prt::HostPool(t - 1);
 	}
-	std::vector<std::thread> th;
-	const size_t per = (bytes / nt + 63) & ~size_t(63);
-	for (size_t k = 1; k < nt; ++k) {
-		const size_t off = k * per;
-		if (off >= bytes)
-			break;
-		th.emplace_back([=] {
-			std::memcpy(static_cast<char *>(dst) + off, static_cast<const char *>(src) + off,
-			            std::min(per, bytes - off));
-		});
-	}
-	std::memcpy(dst, src, std::min(per, bytes));
-	for (auto &t : th)
-		t.join();
+	return slot;
 }
 
-// Rays are cut into chunks that flow through three stages on three streams -- H2D, traversal kernel
-// writing the caller's AoS records, D2H -- over a ring of buffer sets, so both copy engines and
-// the SMs work at the same time.  Pageable host memory (a std::vector) is staged through pinned buffers with a threaded memcpy;
-// pinned / registered host memory is DMA'd directly.
-int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t mask,
-                          const prt_hit_layout *layout, void *hits_out) {
-	if (!c || (n && (!rays6 || !hits_out)))
-		return fail(c, PRT_E_ARG, "nearest_hits: NULL argument");
-	if (mask == 0 || mask > PRT_TAG_ALL)
-		return fail(c, PRT_E_ARG, "nearest_hits: tag mask must be in 1..31");
-	if (int rc = check_layout(c, mask, layout))
-		return rc;
+// Tightly packed device-side record for results that are staged anyway (pageable caller memory):
+// only the requested fields cross PCIe (HitReg<t,primitive_id> is 16 bytes for 8 useful ones,
+// HitReg<valid> 8 for 1); the consumer threads scatter them into the caller's records while they
+// copy.  Word fields first (u, v, t, pid, px, py, pz), the valid byte last.
+struct PackedLayout {
+	prt_hit_layout dev{};   // what the kernel writes
+	int n_words = 0;        // 4-byte fields
+	int32_t src[7], dst[7]; // their offsets in the packed / the caller's record
+	int32_t valid_src = -1, valid_dst = -1;
+};
+
+static PackedLayout make_packed(uint32_t mask, const prt_hit_layout &user) {
+	PackedLayout p;
+	p.dev = prt_hit_layout{0, -1, -1, -1, -1, -1, -1, -1, -1};
+	int32_t at = 0;
+	auto word = [&](int32_t &dev_off, int32_t user_off) {
+		dev_off = at;
+		p.src[p.n_words] = at;
+		p.dst[p.n_words] = user_off;
+		++p.n_words;
+		at += 4;
+	};
+	if (mask & PRT_TAG_UV) {
+		word(p.dev.off_u, user.off_u);
+		word(p.dev.off_v, user.off_v);
+	}
+	if (mask & PRT_TAG_T)
+		word(p.dev.off_t, user.off_t);
+	if (mask & PRT_TAG_PID)
+		word(p.dev.off_pid, user.off_pid);
+	if (mask & PRT_TAG_P) {
+		word(p.dev.off_px, user.off_px);
+		word(p.dev.off_py, user.off_py);
+		word(p.dev.off_pz, user.off_pz);
+	}
+	if (mask & PRT_TAG_VALID) {
+		p.dev.off_valid = at;
+		p.valid_src = at;
+		p.valid_dst = user.off_valid;
+		at += 1;
+	}
+	p.dev.stride = p.n_words ? (uint32_t)((at + 3) & ~3) : (uint32_t)at;
+	return p;
+}
+
+template <int NW, bool V>
+static void scatter_records(const PackedLayout &pl, uint32_t user_stride, const char *src, char *dst,
+                            uint64_t n) {
+	const uint32_t ps = pl.dev.stride;
+	for (uint64_t i = 0; i < n; ++i, src += ps, dst += user_stride) {
+		for (int k = 0; k < NW; ++k) {
+			uint32_t w;
+			std::memcpy(&w, src + pl.src[k], 4);
+			std::memcpy(dst + pl.dst[k], &w, 4);
+		}
+		if (V)
+			dst[pl.valid_dst] = src[pl.valid_src];
+	}
+}
+
+using ScatterFn = void (*)(const PackedLayout &, uint32_t, const char *, char *, uint64_t);
+static ScatterFn scatter_fn(int nw, bool v) {
+	static const ScatterFn table[8][2] = {
+	    {scatter_records<0, false>, scatter_records<0, true>}, {scatter_records<1, false>, scatter_records<1, true>},
+	    {scatter_records<2, false>, scatter_records<2, true>}, {scatter_records<3, false>, scatter_records<3, true>},
+	    {scatter_records<4, false>, scatter_records<4, true>}, {scatter_records<5, false>, scatter_records<5, true>},
+	    {scatter_records<6, false>, scatter_records<6, true>}, {scatter_records<7, false>, scatter_records<7, true>}};
+	return table[nw][v ? 1 : 0];
+}
+
+// One device's share of a host batch.  Rays are cut into chunks that flow through three stages on
+// three streams -- H2D, traversal kernel writing AoS records, D2H -- over a ring of buffer sets, so
+// both copy engines and the SMs work at the same time.  Pinned / registered host memory is DMA'd
+// directly; pageable memory (a std::vector, as in the reference API) is staged through pinned
+// buffers by a producer and a consumer thread, each with its own pool of copy threads, and its
+// results cross PCIe tightly packed.
+static int nearest_hits_device(prt_b200 *c, const float *rays6, uint64_t n, uint32_t mask,
+                               const prt_hit_layout *layout, void *hits_out, int coherence,
+                               int n_devices) {
 	if (n == 0)
 		return PRT_OK;
 	PRT_CUDA(c, cudaSetDevice(c->device));
-	if (int rc = prt::maybe_optimise_tree(c, n))
-		return rc;
-
-	const bool in_pinned = is_pinned(rays6), out_pinned = is_pinned(hits_out);
+	const bool in_pinned = is_pinned(rays6, n * 24);
+	const bool out_pinned = is_pinned(hits_out, n * (size_t)layout->stride);
 	// Chunk schedule: the D2H engine is the bottleneck (records are larger than rays) and starts
 	// only when the first chunk has been uploaded and traced, so small batches are cut into ~8
 	// chunks; every chunk costs launches, a shorter (less efficient) kernel and some idle time of
 	// the copy engines between transfers, so not more.  Chunks are multiples of 2^16 rays (the
-	// reordering threshold) and at most 2^19.  Measured on C2 (2 073 600 rays, pinned buffers,
-	// wall clock per call): 2^16 1.94 ms, 2^17 1.65, 2^18 1.60, n/6 1.69, 2^19 1.72; a small first
+	// reordering threshold) and at most 2^19 (2^21 for batches of >= 2^24 rays, where the ramp-up
+	// no longer matters and reordering works better on larger chunks).  Measured on C2 (2 073 600 rays,
+	// pinned buffers, wall clock per call): 2^16 1.94 ms, 2^17 1.65, 2^18 1.60, n/6 1.69, 2^19 1.72; a small first
 	// chunk followed by doubling ones was slower (the uploads fall behind the downloads), and so
 	// were kernels that read rays / write records through PCIe themselves (2.07 / 9.7 ms).
 	// PRT_B200_CHUNK_LOG2 forces a size.
+	const uint64_t CH_MAX = n >= (1ull << 24) ? (1ull << 21) : (1ull << 19);
 	uint64_t CH = ((n + 7) / 8 + 65535) / 65536 * 65536;
 	if (!in_pinned || !out_pinned)
-		CH = 1ull << 19; // bound by the host-side staging copies: few large ones (4.0 vs 4.6 ms)
+		CH = std::max<uint64_t>(CH, 1ull << 19); // bound by the host-side staging copies: few large ones
 	if (c->chunk_log2 > 0)
 		CH = 1ull << c->chunk_log2;
-	CH = std::min<uint64_t>(std::min<uint64_t>(CH, 1ull << 19), n);
+	CH = std::min<uint64_t>(std::min<uint64_t>(CH, CH_MAX), n);
 	std::vector<uint64_t> start; // chunk k = rays [start[k], start[k+1])
 	for (uint64_t at = 0; at < n; at += CH)
 		start.push_back(at);
 	start.push_back(n);
-	// coherent or not is decided once, on the host copy of the batch (no device probe, no stream
-	// synchronisation inside the pipeline)
 	const auto call0 = std::chrono::steady_clock::now();
-	const int coherence = (c->sort_rays == 2 && n >= 65536) ? prt::host_ray_probe(c, rays6, n) : -1;
-	const double probe_us =
-	    std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - call0).count();
 	constexpr int PIPE = prt_b200::PIPE;
-	const size_t ray_b = 24, hit_b = layout->stride;
+	const PackedLayout packed = make_packed(mask, *layout);
+	const bool use_packed = !out_pinned && c->packed_d2h && packed.dev.stride < layout->stride;
+	const prt_hit_layout dev_layout = use_packed ? packed.dev : *layout;
+	const size_t ray_b = 24, hit_b = layout->stride, dev_hit_b = dev_layout.stride;
 	const uint64_t n_chunks = start.size() - 1;
 	for (int k = 0; k < PIPE && (uint64_t)k < n_chunks; ++k) {
 		PRT_CUDA(c, c->rays_dev[k].reserve(CH * ray_b));
-		PRT_CUDA(c, c->hits_dev[k].reserve(CH * hit_b));
+		PRT_CUDA(c, c->hits_dev[k].reserve(CH * dev_hit_b));
 		if (!in_pinned)
 			PRT_CUDA(c, c->rays_pin[k].reserve(CH * ray_b));
 		if (!out_pinned)
-			PRT_CUDA(c, c->hits_pin[k].reserve(CH * hit_b));
+			PRT_CUDA(c, c->hits_pin[k].reserve(CH * dev_hit_b));
 	}
+	prt::HostPool *pool_in = in_pinned ? nullptr : staging_pool(c, c->pool_in, n_devices);
+	prt::HostPool *pool_out = out_pinned ? nullptr : staging_pool(c, c->pool_out, n_devices);
 	enum { IN = 0, KERN = 1, OUT = 2 };
 	cudaStream_t s_in = c->pipe_stream[IN], s_k = c->pipe_stream[KERN], s_out = c->pipe_stream[OUT];
-	// Pageable caller memory (a std::vector, as in the reference API) is staged through the pinned
-	// ring by two helper threads, so that copying rays in, enqueueing, and copying records out
-	// overlap: `producer` fills rays_pin[b] as soon as the H2D that last used it has left,
-	// `consumer` empties hits_pin[b] as soon as its D2H has arrived.
 	Progress pg;
 	std::thread producer, consumer;
-	struct Joiner { // every exit path: tell the helpers to leave, then wait for them
+	struct Joiner { // every exit path: tell the helpers to leave, wait for them and for the device
 		Progress &pg;
 		std::thread &a, &b;
+		prt_b200 *c;
 		~Joiner() {
 			pg.post([&] { pg.stop = true; });
 			if (a.joinable())
 				a.join();
 			if (b.joinable())
 				b.join();
+			// no copy into the caller's memory may still be in flight once the call has returned
+			for (int k = 0; k < 3; ++k)
+				cudaStreamSynchronize(c->pipe_stream[k]);
 		}
-	} joiner{pg, producer, consumer};
+	} joiner{pg, producer, consumer, c};
 	if (!in_pinned)
 		producer = std::thread([&] {
 			cudaSetDevice(c->device);
@@ -526,13 +862,14 @@ int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t 
 					if (e != cudaSuccess)
 						return pg.fail(e);
 				}
-				par_memcpy(c->rays_pin[b].p, rays6 + start[k] * 6, (start[k + 1] - start[k]) * ray_b);
+				pool_in->copy(c->rays_pin[b].p, rays6 + start[k] * 6, (start[k + 1] - start[k]) * ray_b);
 				pg.post([&] { pg.produced = k + 1; });
 			}
 		});
 	if (!out_pinned)
 		consumer = std::thread([&] {
 			cudaSetDevice(c->device);
+			const ScatterFn scatter = scatter_fn(packed.n_words, packed.valid_src >= 0);
 			for (uint64_t k = 0; k < n_chunks; ++k) {
 				const int b = (int)(k % PIPE);
 				if (!pg.wait([&] { return pg.issued > k; }))
@@ -540,8 +877,18 @@ int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t 
 				const cudaError_t e = cudaEventSynchronize(c->ev_pipe[b][OUT]);
 				if (e != cudaSuccess)
 					return pg.fail(e);
-				par_memcpy(static_cast<char *>(hits_out) + start[k] * hit_b, c->hits_pin[b].p,
-				           (start[k + 1] - start[k]) * hit_b);
+				char *dst = static_cast<char *>(hits_out) + start[k] * hit_b;
+				const uint64_t cnt = start[k + 1] - start[k];
+				if (use_packed) {
+					const char *src = static_cast<const char *>(c->hits_pin[b].p);
+					pool_out->run([&](int part, int parts) {
+						const uint64_t per = (cnt + parts - 1) / parts, lo = std::min(cnt, per * part),
+						               hi = std::min(cnt, lo + per);
+						scatter(packed, layout->stride, src + lo * dev_hit_b, dst + lo * hit_b, hi - lo);
+					});
+				} else {
+					pool_out->copy(dst, c->hits_pin[b].p, cnt * hit_b);
+				}
 				pg.post([&] { pg.consumed = k + 1; });
 			}
 		});
@@ -592,7 +939,7 @@ int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t 
 			PRT_CUDA(c, cudaStreamWaitEvent(s_k, c->ev_pipe[b][OUT], 0));
 		prt::TraceOut out;
 		out.aos = c->hits_dev[b].p;
-		out.layout = *layout;
+		out.layout = dev_layout;
 		out.slot = 0;
 		mark(s_k);
 		int rc = prt::launch_trace(c, c->rays_dev[b].as<float>(), cnt, mask, out, nullptr, s_k,
@@ -610,7 +957,7 @@ int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t 
 		void *dst = out_pinned ? static_cast<void *>(static_cast<char *>(hits_out) + first * hit_b)
 		                       : c->hits_pin[b].p;
 		mark(s_out);
-		PRT_CUDA(c, cudaMemcpyAsync(dst, c->hits_dev[b].p, cnt * hit_b, cudaMemcpyDeviceToHost, s_out));
+		PRT_CUDA(c, cudaMemcpyAsync(dst, c->hits_dev[b].p, cnt * dev_hit_b, cudaMemcpyDeviceToHost, s_out));
 		mark(s_out);
 		PRT_CUDA(c, cudaEventRecord(c->ev_pipe[b][OUT], s_out));
 		pg.post([&] { pg.issued = k + 1; });
@@ -626,14 +973,18 @@ int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t 
 	PRT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
 	PRT_CUDA(c, cudaStreamSynchronize(c->stream));
 	PRT_CUDA(c, cudaEventElapsedTime(&c->last_trace_ms, c->ev0, c->ev1));
+	c->last_h2d_bytes = n * ray_b;
+	c->last_d2h_bytes = n * dev_hit_b;
 	if (c->pipe_trace) {
-		std::fprintf(stderr, "[prt_b200] nearest_hits %llu rays, %llu chunks of %llu, device %.3f ms, "
-		                     "host probe %.0f us, call %.0f us "
+		std::fprintf(stderr, "[prt_b200] dev %d nearest_hits %llu rays, %llu chunks of %llu, device %.3f ms, "
+		                     "call %.0f us, in %s, out %s%s "
 		                     "(chunk: enqueue us | h2d | kernel | d2h, ms since start)\n",
-		             (unsigned long long)n, (unsigned long long)n_chunks, (unsigned long long)CH,
-		             c->last_trace_ms, probe_us,
+		             c->device, (unsigned long long)n, (unsigned long long)n_chunks, (unsigned long long)CH,
+		             c->last_trace_ms,
 		             std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - call0)
-		                 .count());
+		                 .count(),
+		             in_pinned ? "pinned" : "pageable", out_pinned ? "pinned" : "pageable",
+		             use_packed ? " (packed)" : "");
 		for (uint64_t k = 0; k < n_chunks; ++k) {
 			float t[6];
 			for (int j = 0; j < 6; ++j)
@@ -646,6 +997,48 @@ int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t 
 	}
 	return PRT_OK;
 }
+
+extern "C" {
+
+int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t mask,
+                          const prt_hit_layout *layout, void *hits_out) {
+	if (!c || (n && (!rays6 || !hits_out)))
+		return fail(c, PRT_E_ARG, "nearest_hits: NULL argument");
+	if (mask == 0 || mask > PRT_TAG_ALL)
+		return fail(c, PRT_E_ARG, "nearest_hits: tag mask must be in 1..31");
+	if (int rc = check_layout(c, mask, layout))
+		return rc;
+	if (n == 0)
+		return PRT_OK;
+	PRT_CUDA(c, cudaSetDevice(c->device));
+	// coherent or not is decided once, on the host copy of the batch (no device probe, no stream
+	// synchronisation inside the pipeline)
+	const int coherence = (c->sort_rays == 2 && n >= 65536) ? prt::host_ray_probe(c, rays6, n) : -1;
+	const int G = 1 + (int)c->peers.size();
+	// Multi-GPU: device i takes the contiguous slice [i*n/G, (i+1)*n/G) and writes its records at
+	// the slice's offset in the caller's array -- the hits come back in ray order with no gather
+	// step.  Every device counts the WHOLE batch towards its lazy tree optimisation, so that all
+	// replicas are optimised before the same call.
+	const int rc = on_all_devices(c, [&](prt_b200 *d, int i) -> int {
+		if (int r = prt::maybe_optimise_tree(d, n))
+			return r;
+		const uint64_t lo = n * (uint64_t)i / G, hi = n * (uint64_t)(i + 1) / G;
+		return nearest_hits_device(d, rays6 + lo * 6, hi - lo, mask, layout,
+		                           static_cast<char *>(hits_out) + lo * (size_t)layout->stride, coherence,
+		                           G);
+	});
+	if (rc)
+		return rc;
+	for (prt_b200 *d : c->peers) {
+		c->last_trace_ms = std::max(c->last_trace_ms, d->last_trace_ms);
+		c->last_h2d_bytes += d->last_h2d_bytes;
+		c->last_d2h_bytes += d->last_d2h_bytes;
+	}
+	return PRT_OK;
+}
+
+uint64_t prt_b200_last_h2d_bytes(const prt_b200 *c) { return c ? c->last_h2d_bytes : 0; }
+uint64_t prt_b200_last_d2h_bytes(const prt_b200 *c) { return c ? c->last_d2h_bytes : 0; }
 
 // Pinned host memory for callers that want the host entry points to DMA directly (no staging).
 void *prt_b200_alloc_pinned(size_t bytes) {

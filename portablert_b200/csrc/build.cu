@@ -694,7 +694,8 @@ __global__ void __launch_bounds__(256)
 	int32_t me = ~j, cur = leaf_parent[j];
 	float acc = 0.0f;
 	for (;;) {
-		const int4 tail = __ldg(reinterpret_cast<const int4 *>(nodes + cur) + 3); // topology is fixed
+		// (topology is fixed, but the 32-byte sector is written by other threads: no ld.global.nc)
+		const int4 tail = __ldcg(reinterpret_cast<const int4 *>(nodes + cur) + 3);
 		const int side = tail.y == me ? 1 : 0;
 		float2 *nd = reinterpret_cast<float2 *>(nodes + cur) + (side ? 3 : 0);
 		nd[0] = make_float2(b.lo[0], b.lo[1]);
@@ -1000,6 +1001,7 @@ int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 
 	const int stream_grid = (int)std::min<uint64_t>((n + TT - 1) / TT, (uint64_t)c->sm_count * 8);
 	const int bits = morton_bits_for(n);
+	c->morton_bits = bits;
 
 	k_bounds_init<<<1, 32, 0, s>>>(c->bounds.as<uint32_t>());
 	k_bounds<<<stream_grid, TT, 0, s>>>(d_tris9, n, c->bounds.as<uint32_t>());

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <vector>
 
 #include "../../include/prt_b200.h"
 #include "prt_math.cuh"
@@ -37,6 +38,10 @@ struct DevBuf {
 		p = nullptr;
 		cap = 0;
 	}
+	DevBuf() = default;
+	DevBuf(const DevBuf &) = delete;
+	DevBuf &operator=(const DevBuf &) = delete;
+	~DevBuf() { release(); } // (members of the context: a new buffer cannot be forgotten in destroy)
 	template <class T> T *as() const { return static_cast<T *>(p); }
 };
 
@@ -61,13 +66,21 @@ struct PinnedBuf {
 		p = nullptr;
 		cap = 0;
 	}
+	PinnedBuf() = default;
+	PinnedBuf(const PinnedBuf &) = delete;
+	PinnedBuf &operator=(const PinnedBuf &) = delete;
+	~PinnedBuf() { release(); }
 };
+
+class HostPool; // prt_hostpool.h: worker threads that stage pageable caller memory
+struct NcclApi; // api.cu: libnccl entry points resolved at run time
 
 } // namespace prt
 
 struct prt_b200 {
 	int device = -1;
 	int sm_count = 0;
+	uint64_t l2_bytes = 0;
 	cudaStream_t stream = nullptr;
 	// host entry point: one stream per pipeline stage (H2D, kernels, D2H) over a ring of
 	// PIPE chunk buffers; ev_pipe[b][stage] = "that stage has left buffer set b"
@@ -77,6 +90,20 @@ struct prt_b200 {
 	cudaEvent_t ev_pipe[PIPE][3] = {};
 	std::string name;
 	std::string err;
+
+	// multi-GPU (prt_b200_create_multi / env PRT_B200_GPUS): the context the caller holds drives
+	// device `device` itself and owns one sub-context per further device; the scene is replicated
+	// (triangles broadcast over NVLink, identical deterministic build everywhere) and every host
+	// batch is cut into contiguous slices, one per device
+	std::vector<prt_b200 *> peers;
+	prt::NcclApi *nccl = nullptr;     // resolved lazily at the first broadcast (owner only)
+	std::vector<void *> nccl_comms;   // ncclComm_t per device, [0] = this context
+	int bcast_mode = 0;               // env PRT_B200_BCAST: 0 NCCL when loadable else peer copies, 1 peer copies
+	std::string bcast_used;           // what the last broadcast went through ("nccl", "p2p")
+	// host staging workers (pageable caller memory -> pinned ring and back), created on first use
+	prt::HostPool *pool_in = nullptr, *pool_out = nullptr;
+	int copy_threads = 0;             // env PRT_B200_COPY_THREADS (0 = automatic)
+	int bps_cache[32][8] = {};        // resident blocks per SM of each traversal kernel variant
 
 	// scene
 	uint64_t n_tris = 0;
@@ -106,6 +133,16 @@ struct prt_b200 {
 
 	// trace scratch
 	prt::DevBuf rays_dev[PIPE], hits_dev[PIPE], counter;
+	prt::DevBuf stack_ovf[2]; // overflow of the shared-memory traversal stacks, per launch slot
+	prt::DevBuf slow_list[2]; // rays the fast kernel set aside for the exact kernel, per launch slot
+	// the exact pass of the last EXOTIC_DEFERRED launch (trace.cu: finish_exotic)
+	bool pending_exotic = false;
+	alignas(16) unsigned char exotic_blob[384] = {}; // its TraceParams
+	const void *exotic_fn = nullptr;
+	int exotic_cache_slot = 0, exotic_slot = 0;
+	uint32_t exotic_mask = 0;
+	uint64_t exotic_rays = 0; // rays traced by the exact pass so far
+	int morton_bits = 0;      // bits per axis of the current tree's Morton keys
 	// ray reordering scratch, one set per launch slot (concurrent launches on different streams)
 	struct RaySort {
 		prt::DevBuf keys[2], vals[2], scratch;
@@ -127,10 +164,14 @@ struct prt_b200 {
 	bool recs_vertex_form = false;           // the current triangle records hold v1, v2 (watertight) instead of the edges
 	int fast_boxes = 1;                      // env PRT_B200_FAST_BOXES=0 forces the exact test everywhere
 	int refill = 16;                         // env PRT_B200_REFILL: dynamic ray-fetch threshold (lanes)
+	int leaf_votes = 8;                      // env PRT_B200_LEAF_VOTES: lanes waiting at a triangle that start a leaf phase
+	int prefetch = 2;                        // env PRT_B200_PREFETCH: 0 never, 1 always, 2 when the BVH exceeds L2
+	bool packed_d2h = true;                  // env PRT_B200_PACKED_D2H: pageable results come back tightly packed
 	int chunk_log2 = 0; // host entry point: rays per pipeline chunk (0 = automatic)
 	bool pipe_trace = false; // env PRT_B200_PIPE_TRACE: print the stage timeline of every host call
 	uint64_t launches = 0;
 	float last_build_ms = 0.f, last_trace_ms = 0.f;
+	uint64_t last_h2d_bytes = 0, last_d2h_bytes = 0; // what the last host call moved over PCIe
 };
 
 namespace prt {
@@ -171,9 +212,13 @@ struct TraceOut {
 	int slot = 0; // which ray counter to use (concurrent launches on different streams)
 };
 // coherence: -1 = probe the batch on the device (one stream synchronisation), 0 = known coherent,
-// 1 = known incoherent (reorder it)
+// 1 = known incoherent (reorder it); exotic_mode: how the rays the fast kernel cannot take reach
+// the exact kernel (trace.cu)
+enum { EXOTIC_INLINE = 0, EXOTIC_DEFERRED = 1 };
 int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, const TraceOut &out,
-                 uint32_t *d_counts, cudaStream_t stream, int coherence = -1);
+                 uint32_t *d_counts, cudaStream_t stream, int coherence = -1,
+                 int exotic_mode = EXOTIC_INLINE);
+int finish_exotic(prt_b200 *c, cudaStream_t stream, bool *ran);
 int host_ray_probe(const prt_b200 *c, const float *rays6, uint64_t n);
 
 // sort.cu

@@ -13,6 +13,7 @@
 // AoS} output; only the requested fields are tracked and written.  Warps are persistent and pull
 // 32-ray packets from a global counter.
 #include <algorithm>
+#include <cstring>
 
 #include "prt_trace_kernel.cuh"
 
@@ -124,22 +125,7 @@ static void k_ray_probe_launch(prt_b200 *c, const float *rays, uint64_t n, float
 constexpr uint64_t SORT_MIN_RAYS = 1u << 16;
 
 
-template <uint32_t M> struct Table {
-	static void fill(KernelFn (*t)[4]) {
-		t[M][0] = k_trace<M, false, false, false>;
-		t[M][1] = k_trace<M, true, false, false>;
-		t[M][2] = k_trace<M, false, false, true>;
-		t[M][3] = k_trace<M, true, false, true>;
-		Table<M - 1>::fill(t);
-	}
-};
-template <> struct Table<0> {
-	static void fill(KernelFn (*)[4]) {}
-};
-
-static KernelFn g_table[32][4];
-static int g_blocks_per_sm[32][6]; // [4], [5]: watertight SoA / AoS (trace_wt.cu)
-static bool g_table_ready = false;
+KernelFn trace_kernel_fast(uint32_t mask, bool aos) { return kernel_of<false, false, false>(mask, aos); }
 
 static void scene_grid(const prt_b200 *c, float3 &lo, float3 &ie) {
 	lo = make_float3(c->scene_lo[0], c->scene_lo[1], c->scene_lo[2]);
@@ -172,19 +158,56 @@ int host_ray_probe(const prt_b200 *c, const float *rays6, uint64_t n) {
 	return same * 2 < segs * 31 ? 1 : 0;
 }
 
+// Upper bound of the traversal stack depth for the current tree: one entry per level of the
+// current path.  Radix tree over (3*bits-bit key . index): height <= 3*bits + bit length of n;
+// an optimised tree has its height measured by the treelet kernel.  Wide nodes push up to three
+// entries per two levels.
+static int stack_bound(const prt_b200 *c, bool wide) {
+	int bitlen = 0;
+	for (uint64_t n = c->n_tris; n; n >>= 1)
+		++bitlen;
+	int depth = std::min(96, 3 * c->morton_bits + bitlen + 2);
+	if (c->tree_optimised && c->tree_depth > 0)
+		depth = std::min(96, (int)c->tree_depth + 1);
+	return wide ? 3 * ((depth + 1) / 2) + 3 : depth;
+}
+
+static int launch_kernel(prt_b200 *c, KernelFn fn, int cache_slot, uint32_t mask, TraceParams &P,
+                         uint64_t n, bool wide, int slot, cudaStream_t s) {
+	int bps = cache_slot >= 0 ? c->bps_cache[mask][cache_slot] : 0;
+	if (bps == 0) {
+		PRT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, TRACE_THREADS, 0));
+		if (bps < 1)
+			bps = 1;
+		if (cache_slot >= 0)
+			c->bps_cache[mask][cache_slot] = bps;
+	}
+	const uint64_t want = (n + TRACE_THREADS - 1) / TRACE_THREADS;
+	const uint64_t grid = std::min<uint64_t>(want, (uint64_t)c->sm_count * bps);
+	// stack overflow area: sized for the largest grid this context launches and the current tree
+	const uint64_t threads = (uint64_t)c->sm_count * 16 * TRACE_THREADS;
+	const int deep = std::max(1, stack_bound(c, wide) - SMEM_STACK + 1);
+	PRT_CUDA(c, c->stack_ovf[slot].reserve(threads * (uint64_t)deep * sizeof(uint2)));
+	P.stack_ovf = c->stack_ovf[slot].as<uint2>();
+	P.ovf_stride = (uint32_t)threads;
+	fn<<<(unsigned)grid, TRACE_THREADS, 0, s>>>(P);
+	c->launches += 1;
+	PRT_CUDA(c, cudaGetLastError());
+	return PRT_OK;
+}
+
+// mode of the second (exact) pass over the rays the fast kernel set aside:
+//   EXOTIC_INLINE    launched unconditionally right behind the fast kernel (host pipeline: no
+//                    synchronisation point between chunks; an empty pass costs a few microseconds)
+//   EXOTIC_DEFERRED  the caller synchronises the stream and then calls finish_exotic(), which
+//                    launches the pass only if the fast kernel reported set-aside rays
 int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, const TraceOut &out,
-                 uint32_t *d_counts, cudaStream_t s, int coherence) {
+                 uint32_t *d_counts, cudaStream_t s, int coherence, int exotic_mode) {
 	if (mask == 0 || mask > PRT_TAG_ALL)
 		return fail(c, PRT_E_ARG, "nearest_hits: tag mask must be in 1..31");
+	c->pending_exotic = false;
 	if (n == 0)
 		return PRT_OK;
-	if (!g_table_ready) {
-		Table<31>::fill(g_table);
-		for (int m = 1; m < 32; ++m)
-			for (int a = 0; a < 6; ++a)
-				g_blocks_per_sm[m][a] = 0;
-		g_table_ready = true;
-	}
 	TraceParams P{};
 	P.nodes = c->nodes.as<Node>();
 	P.nodes4 = c->nodes4.as<Node4>();
@@ -206,10 +229,11 @@ int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, c
 	P.slack_ulps = c->opts.slack_ulps;
 	for (int a = 0; a < 3; ++a)
 		P.scene_absmax[a] = c->scene_absmax[a];
-	P.fast = c->fast_boxes;
 	P.refill = c->refill;
-	// [0] ray counter, [1] coherence-probe count, [2] warps that left: zeroed at create, re-armed by
-	// the kernel itself (32 bytes per launch slot)
+	P.leaf_votes = c->leaf_votes;
+	P.rays_vec = (reinterpret_cast<uintptr_t>(d_rays6) & 7) == 0;
+	// [0] ray counter, [1] coherence-probe count, [2] warps that left, [3] rays set aside: zeroed at
+	// create, re-armed by the kernels themselves (32 bytes per launch slot)
 	P.counter = c->counter.as<unsigned long long>() + 4 * out.slot;
 
 	// ---- optional ray reordering (see k_ray_keys)
@@ -244,8 +268,6 @@ int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, c
 			    d_rays6, n, lo, ie, c->ray_key_ob, c->ray_key_db, rs.keys[0].as<uint64_t>(),
 			    rs.vals[0].as<uint32_t>());
 			c->launches += 1;
-		}
-		if (do_sort) {
 			uint64_t *const kk[2] = {rs.keys[0].as<uint64_t>(), rs.keys[1].as<uint64_t>()};
 			uint32_t *const vv[2] = {rs.vals[0].as<uint32_t>(), rs.vals[1].as<uint32_t>()};
 			int cur = 0;
@@ -267,34 +289,84 @@ int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, c
 	// instrumented count launch follows the choice made for the last traced batch)
 	// (the watertight mode keeps to the binary nodes: its records hold vertices, see build.cu)
 	const bool wt = c->recs_vertex_form;
-	const bool have_wide = c->n_nodes && c->wide_built && !wt;
+	const bool aos = out.aos != nullptr;
+	const bool have_wide = c->n_nodes && c->wide_built && !wt && c->fast_boxes;
 	const bool wide = have_wide && (c->wide_mode == 1 ||
 	                                (c->wide_mode == 2 && (d_counts ? c->last_wide : P.perm != nullptr)));
 	if (!d_counts)
 		c->last_wide = wide;
-	const int variant = (out.aos != nullptr ? 1 : 0) + (wt ? 4 : (wide ? 2 : 0));
-	KernelFn fn = wt ? trace_kernel_wt(mask, out.aos != nullptr, d_counts != nullptr)
-	                 : d_counts ? (wide ? (KernelFn)k_trace<PRT_TAG_ALL, false, true, true>
-	                                    : (KernelFn)k_trace<PRT_TAG_ALL, false, true, false>)
-	                            : g_table[mask][variant];
-	int bps = d_counts ? 0 : g_blocks_per_sm[mask][variant];
-	if (bps == 0) {
-		PRT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, TRACE_THREADS, 0));
-		if (bps < 1)
-			bps = 1;
-		if (!d_counts)
-			g_blocks_per_sm[mask][variant] = bps;
-	}
 	if (wide)
 		c->wide_batches++;
-	uint64_t want = (n + TRACE_THREADS - 1) / TRACE_THREADS;
-	uint64_t grid = (uint64_t)c->sm_count * bps;
-	if (want < grid)
-		grid = want;
-	fn<<<(unsigned)grid, TRACE_THREADS, 0, s>>>(P);
-	c->launches += 1;
-	PRT_CUDA(c, cudaGetLastError());
-	return PRT_OK;
+	// nodes pushed on the stack are prefetched into L2 when the tree cannot live there
+	const uint64_t tree_bytes = c->n_nodes * 64 + c->n_tris * 64;
+	P.prefetch = c->prefetch == 1 || (c->prefetch == 2 && c->l2_bytes && tree_bytes > c->l2_bytes);
+
+	if (d_counts) { // instrumented run: set-aside rays (if any) count as zero
+		PRT_CUDA(c, cudaMemsetAsync(d_counts, 0, n * 8, s));
+		P.slow_cap = 0;
+		if (int rc = launch_kernel(c, trace_kernel_count(wide, wt), -1, mask, P, n, wide, out.slot, s))
+			return rc;
+		// its set-aside counter is not consumed by an exact pass: re-arm it
+		PRT_CUDA(c, cudaMemsetAsync(P.counter + 3, 0, 8, s));
+		return PRT_OK;
+	}
+	if (!c->fast_boxes) // the reference's box arithmetic everywhere
+		return launch_kernel(c, wt ? trace_kernel_wt_exact(mask, aos) : trace_kernel_exact(mask, aos),
+		                     (wt ? 6 : 4) + (aos ? 1 : 0), mask, P, n, false, out.slot, s);
+
+	// ---- fast kernel; the rays it cannot take go to a list
+	const uint64_t cap = n < (1ull << 32) ? std::min<uint64_t>(n, 1ull << 20) : 0;
+	PRT_CUDA(c, c->slow_list[out.slot].reserve(std::max<uint64_t>(cap, 1) * 4));
+	P.slow_list = c->slow_list[out.slot].as<uint32_t>();
+	P.slow_cap = (uint32_t)cap;
+	volatile unsigned long long *flag = c->probe_host + 2 + out.slot;
+	if (exotic_mode == EXOTIC_DEFERRED) {
+		*flag = 0;
+		P.slow_host = c->probe_dev + 2 + out.slot;
+	}
+	// bps_cache columns: 0/1 fast SoA/AoS, 2/3 wide, 4/5 exact, 6/7 watertight exact; the watertight
+	// fast kernels share 2/3 (a watertight scene never uses the wide nodes)
+	KernelFn fn = wt ? trace_kernel_wt(mask, aos)
+	                 : (wide ? trace_kernel_wide(mask, aos) : trace_kernel_fast(mask, aos));
+	if (int rc = launch_kernel(c, fn, (aos ? 1 : 0) + ((wt || wide) ? 2 : 0), mask, P, n, wide,
+	                           out.slot, s))
+		return rc;
+	// ---- exact pass over the set-aside rays
+	P.slow_count = P.counter + 3;
+	P.slow_host = nullptr;
+	P.prefetch = 0;
+	static_assert(sizeof(TraceParams) <= sizeof(c->exotic_blob), "exotic_blob too small");
+	std::memcpy(c->exotic_blob, &P, sizeof P);
+	const KernelFn exact_fn = wt ? trace_kernel_wt_exact(mask, aos) : trace_kernel_exact(mask, aos);
+	c->exotic_fn = reinterpret_cast<const void *>(exact_fn);
+	c->exotic_cache_slot = (wt ? 6 : 4) + (aos ? 1 : 0);
+	c->exotic_mask = mask;
+	c->exotic_slot = out.slot;
+	if (exotic_mode == EXOTIC_DEFERRED) {
+		c->pending_exotic = true;
+		return PRT_OK;
+	}
+	return launch_kernel(c, exact_fn, c->exotic_cache_slot, mask, P, n, false, out.slot, s);
+}
+
+// After the stream of a EXOTIC_DEFERRED launch has been synchronised: trace the set-aside rays, if
+// the fast kernel reported any.  *ran says whether a kernel was launched (the caller then
+// synchronises again).
+int finish_exotic(prt_b200 *c, cudaStream_t s, bool *ran) {
+	*ran = false;
+	if (!c->pending_exotic)
+		return PRT_OK;
+	c->pending_exotic = false;
+	volatile unsigned long long *flag = c->probe_host + 2 + c->exotic_slot;
+	const unsigned long long set_aside = *flag ? *flag - 1 : 0;
+	if (set_aside == 0)
+		return PRT_OK;
+	*ran = true;
+	c->exotic_rays += set_aside;
+	TraceParams P;
+	std::memcpy(&P, c->exotic_blob, sizeof P);
+	return launch_kernel(c, reinterpret_cast<KernelFn>(const_cast<void *>(c->exotic_fn)),
+	                     c->exotic_cache_slot, c->exotic_mask, P, P.n_rays, false, c->exotic_slot, s);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -326,8 +326,8 @@ void emu_trace(void *h, const float *rays6, uint64_t n, int prune, float slack_r
 	for (uint64_t i = 0; i < n; ++i) {
 		RayC r = make_ray(rays6 + 6 * i);
 		Hit hit;
-		const FastRay fr = make_fast_ray(r, e->absmax);
-		const bool f = fast && fr.ok; // per ray here; the kernel votes per warp
+		const FastRay fr = make_fast_ray(r, e->absmax, wide != 0 && !wt);
+		const bool f = fast && fr.ok; // rays that do not qualify go to the exact kernel
 		const Node4 *n4 = e->nodes4.data();
 		if (wt && anyhit && f)
 			traverse<true, false, false, false, true, false, true>(e->nodes.data(), e->tris.data(), e->n, e->root, r, fr, o, hit);

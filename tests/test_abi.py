@@ -25,7 +25,7 @@ def test_exports_every_declared_symbol():
     for n in names:
         assert hasattr(raw, n), f"libprt_b200.so does not export {n}"
     assert sorted(_lib.SYMBOLS) == names, "python binding table out of sync with the header"
-    assert prt.lib().prt_b200_abi_version() == 2
+    assert prt.lib().prt_b200_abi_version() == 3
 
 
 def test_library_contains_sm100a_code_only():

@@ -50,7 +50,11 @@ def test_emulated_kernels_match_oracle(name, oracle, emu):
         slow = emu.trace(rays, prune=0, fast=False)
         if len(tris) > 1:  # (a single-triangle scene carries a never-hit dummy sibling record)
             assert np.array_equal(slow["counts"][gen, 1], ref["visits"][gen, 1])
-        assert (exact["counts"][:, 1] >= slow["counts"][:, 1]).all()  # fast test: conservative
+        # fast test: conservative.  (A ray with a zero direction component lying exactly in a face
+        # plane of a box is the reference's 0*inf = NaN class: its arithmetic then passes that box
+        # whatever the other axes say, the fast test keeps testing them -- results are unaffected,
+        # asserted above, because a triangle Moeller-Trumbore accepts is met by the line.)
+        assert (exact["counts"][gen, 1] >= slow["counts"][gen, 1]).all()
         pruned = emu.trace(rays, prune=1)
         for k in ("t", "u", "v", "pid", "valid"):
             assert np.array_equal(pruned[k], exact[k], equal_nan=True), (name, k)
@@ -143,8 +147,10 @@ def test_fast_box_test_is_conservative_and_changes_nothing(emu, oracle):
             assert f.mean() > 0.9
             if prune == 0:
                 # visits can only grow: the fast test never rejects what the exact one passes
-                assert (fast["counts"][:, 1] >= exact["counts"][:, 1]).all()
-                assert (fast["counts"][:, 0] >= exact["counts"][:, 0]).all()
+                # (outside the reference's 0*inf = NaN class, see above)
+                gen = ~(rays[:, 3:6] == 0).any(1)
+                assert (fast["counts"][gen, 1] >= exact["counts"][gen, 1]).all()
+                assert (fast["counts"][gen, 0] >= exact["counts"][gen, 0]).all()
             # ... and only a little (with pruning the visit ORDER may differ slightly too)
             assert fast["counts"].sum() <= 1.02 * exact["counts"].sum() + 10
     # far-away origin: the margin grows with |o| and must still be conservative
