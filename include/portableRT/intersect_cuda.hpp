@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "backend.hpp"
@@ -28,6 +29,28 @@
 #include "prt_b200.h"
 
 namespace portableRT {
+
+namespace cuda_detail {
+// std::vector<H>(n) value-initialises: for the result of a 100 M-ray call that is 1.6 GB written
+// (and page-faulted) by one thread before the first ray is traced, only to be overwritten.  The
+// records are trivial, so the vector's storage is reserved and its size set without touching it
+// (libstdc++: vector<T> : protected _Vector_base<T> whose _M_impl holds start/finish/end); the
+// library's staging threads are then the first to touch each page, in parallel.  Other standard
+// libraries, or -DPRT_B200_NO_VECTOR_HACK, take the plain value-initialising path.
+template <class T> struct VectorAccess : std::vector<T> {
+	static void set_size(std::vector<T> &v, std::size_t n) {
+#if defined(__GLIBCXX__) && !defined(PRT_B200_NO_VECTOR_HACK) && !defined(_GLIBCXX_DEBUG)
+		static_assert(std::is_trivially_copyable<T>::value && std::is_trivially_destructible<T>::value,
+		              "HitReg records are trivial");
+		v.reserve(n);
+		auto &a = static_cast<VectorAccess &>(v);
+		a._M_impl._M_finish = a._M_impl._M_start + n;
+#else
+		v.resize(n);
+#endif
+	}
+};
+} // namespace cuda_detail
 
 class CUDABackend : public InvokableBackend<CUDABackend> {
   public:
@@ -67,6 +90,13 @@ class CUDABackend : public InvokableBackend<CUDABackend> {
 		check(prt_b200_set_tris(m_ctx, tris.empty() ? nullptr : tris.data()->data(), tris.size()));
 	}
 
+	// The move overload the reference leaves as a TODO (backend.hpp:18): the triangles live on the
+	// device after the call, so the caller's storage is released.
+	void set_tris(Tris &&tris) {
+		set_tris(static_cast<const Tris &>(tris));
+		Tris().swap(tris);
+	}
+
 	std::string device_name() const override {
 		char buf[256] = "unavailable";
 		if (m_ctx)
@@ -78,14 +108,17 @@ class CUDABackend : public InvokableBackend<CUDABackend> {
 	std::vector<HitReg<Tags...>> nearest_hits(const std::vector<Ray> &rays) {
 		using H = HitReg<Tags...>;
 		static_assert(sizeof(Ray) == 24, "Ray is 6 packed floats (core.hpp:19-22)");
-		std::vector<H> hits(rays.size());
+		std::vector<H> hits;
 		constexpr uint32_t mask = (H::has_uv::value ? PRT_TAG_UV : 0u) | (H::has_t::value ? PRT_TAG_T : 0u) |
 		                          (H::has_primitive_id::value ? PRT_TAG_PID : 0u) |
 		                          (H::has_p::value ? PRT_TAG_P : 0u) |
 		                          (H::has_valid::value ? PRT_TAG_VALID : 0u);
-		if (mask == 0 || rays.empty())
-			return hits; // HitReg<> has no fields to fill
+		if (mask == 0 || rays.empty()) {
+			hits.resize(rays.size()); // HitReg<> has no fields to fill
+			return hits;
+		}
 		need_ctx();
+		cuda_detail::VectorAccess<H>::set_size(hits, rays.size()); // every requested field is written below
 		const prt_hit_layout lay = layout<H>();
 		check(prt_b200_nearest_hits(m_ctx, rays.data()->origin.data(), rays.size(), mask, &lay,
 		                            hits.data()));

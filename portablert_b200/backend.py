@@ -61,10 +61,15 @@ def _layout_struct(mask: int) -> HitLayout:
 class CUDABackend(Backend):
     """The B200-native backend ("CUDA"), sibling of the reference's CPU/OptiX/HIP/SYCL/Embree ones."""
 
-    def __init__(self, device: int | None = None):
+    def __init__(self, device: int | None = None, gpus: int | None = None):
+        """device: CUDA device index (None: env PRT_B200_DEVICE / the first CC 10.x device).
+        gpus: number of GPUs this one backend spreads over inside the library (None: env
+        PRT_B200_GPUS, default 1) -- the scene is replicated over NVLink, host ray batches are cut
+        into contiguous slices, hits come back in ray order (prt_b200_create_multi)."""
         super().__init__("CUDA")
         self._h = C.c_void_p()
         self._device = device
+        self._gpus = gpus
 
     # --- Backend virtuals -----------------------------------------------------------------------
     def is_available(self) -> bool:
@@ -75,10 +80,11 @@ class CUDABackend(Backend):
         examples/validation/main.cpp:242)."""
         if self._h:
             return
-        dev = self._device
-        if dev is None:
-            dev = int(os.environ.get("PRT_B200_DEVICE", "-1"))
-        rc = lib().prt_b200_create(C.byref(self._h), dev)
+        if self._gpus is not None:
+            rc = lib().prt_b200_create_multi(C.byref(self._h), int(self._gpus))
+        else:
+            dev = -1 if self._device is None else int(self._device)
+            rc = lib().prt_b200_create(C.byref(self._h), dev)
         if rc:
             self._h = C.c_void_p()
             raise RuntimeError("CUDA backend init failed: " + lib().prt_b200_last_error(None).decode())
@@ -229,6 +235,23 @@ class CUDABackend(Backend):
 
     # --- introspection --------------------------------------------------------------------------
     @property
+    def num_devices(self) -> int:
+        self._need()
+        return int(lib().prt_b200_num_devices(self._h))
+
+    @property
+    def broadcast_path(self) -> str:
+        """what the last multi-GPU set_tris moved the triangles with: "nccl", "p2p" or "" """
+        self._need()
+        return lib().prt_b200_broadcast_path(self._h).decode()
+
+    @property
+    def last_transfer_bytes(self):
+        """(host->device, device->host) bytes of the last nearest_hits call"""
+        self._need()
+        return (int(lib().prt_b200_last_h2d_bytes(self._h)), int(lib().prt_b200_last_d2h_bytes(self._h)))
+
+    @property
     def num_tris(self):
         return lib().prt_b200_num_tris(self._h)
 
@@ -255,6 +278,19 @@ class CUDABackend(Backend):
     @property
     def last_trace_ms(self):
         return lib().prt_b200_last_trace_ms(self._h)
+
+    @property
+    def last_kernel_ms(self):
+        """the traversal kernel of the last trace_dev* call alone (without ray reordering)"""
+        return lib().prt_b200_last_kernel_ms(self._h)
+
+    @property
+    def exotic_rays(self):
+        return lib().prt_b200_exotic_rays(self._h)
+
+    @property
+    def l2_bytes(self):
+        return lib().prt_b200_l2_bytes(self._h)
 
     def download_bvh(self):
         """-> (nodes (n_nodes,16) float32 view of the 64-byte nodes, tris (n_tris,16) float32: the 64-byte records)."""

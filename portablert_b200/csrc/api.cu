@@ -9,6 +9,7 @@
 #include <condition_variable>
 #include <cstring>
 #include <dlfcn.h>
+#include <sys/mman.h>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -159,6 +160,10 @@ static int create_one(prt_b200 **out, int device) {
 		e = cudaEventCreate(&c->ev0);
 	if (e == cudaSuccess)
 		e = cudaEventCreate(&c->ev1);
+	if (e == cudaSuccess)
+		e = cudaEventCreate(&c->ev_k0);
+	if (e == cudaSuccess)
+		e = cudaEventCreate(&c->ev_k1);
 	for (int k = 0; k < prt_b200::PIPE && e == cudaSuccess; ++k)
 		for (int j = 0; j < 3 && e == cudaSuccess; ++j)
 			e = cudaEventCreateWithFlags(&c->ev_pipe[k][j], cudaEventDisableTiming);
@@ -209,6 +214,10 @@ static int create_one(prt_b200 **out, int device) {
 		c->refill = std::max(0, std::min(32, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_LEAF_VOTES"))
 		c->leaf_votes = std::max(1, std::min(32, std::atoi(e)));
+	if (const char *e = std::getenv("PRT_B200_COOP"))
+		c->coop_after = std::max(0, std::min(1 << 20, std::atoi(e)));
+	if (const char *e = std::getenv("PRT_B200_COOP_BLOCKS"))
+		c->coop_blocks = std::max(1, std::min(8, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_PREFETCH"))
 		c->prefetch = std::max(0, std::min(2, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_COPY_THREADS"))
@@ -362,6 +371,10 @@ void prt_b200_destroy(prt_b200 *c) {
 		cudaEventDestroy(c->ev0);
 	if (c->ev1)
 		cudaEventDestroy(c->ev1);
+	if (c->ev_k0)
+		cudaEventDestroy(c->ev_k0);
+	if (c->ev_k1)
+		cudaEventDestroy(c->ev_k1);
 	if (c->stream)
 		cudaStreamDestroy(c->stream);
 	delete c; // DevBuf / PinnedBuf members release their memory (prt_ctx.h)
@@ -621,6 +634,9 @@ static int timed_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t m
 	PRT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
 	PRT_CUDA(c, cudaStreamSynchronize(c->stream));
 	PRT_CUDA(c, cudaEventElapsedTime(&c->last_trace_ms, c->ev0, c->ev1));
+	c->last_kernel_ms = 0.f;
+	if (n)
+		PRT_CUDA(c, cudaEventElapsedTime(&c->last_kernel_ms, c->ev_k0, c->ev_k1));
 	// rays the fast kernel set aside (non-finite / overflowing components): exact kernel, timed too
 	bool ran = false;
 	PRT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
@@ -1014,6 +1030,16 @@ int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t 
 	// coherent or not is decided once, on the host copy of the batch (no device probe, no stream
 	// synchronisation inside the pipeline)
 	const int coherence = (c->sort_rays == 2 && n >= 65536) ? prt::host_ray_probe(c, rays6, n) : -1;
+	// A large pageable result (a fresh std::vector) is about to be touched for the first time by
+	// the staging threads: ask for transparent huge pages first (512x fewer page faults where the
+	// kernel allows it; harmless otherwise)
+	if ((size_t)n * layout->stride >= (size_t(16) << 20) && !is_pinned(hits_out, 1)) {
+		const uintptr_t lo = (reinterpret_cast<uintptr_t>(hits_out) + (2u << 20) - 1) & ~uintptr_t((2u << 20) - 1);
+		const uintptr_t hi = (reinterpret_cast<uintptr_t>(hits_out) + (size_t)n * layout->stride) &
+		                     ~uintptr_t((2u << 20) - 1);
+		if (hi > lo)
+			madvise(reinterpret_cast<void *>(lo), hi - lo, MADV_HUGEPAGE);
+	}
 	const int G = 1 + (int)c->peers.size();
 	// Multi-GPU: device i takes the contiguous slice [i*n/G, (i+1)*n/G) and writes its records at
 	// the slice's offset in the caller's array -- the hits come back in ray order with no gather
@@ -1112,6 +1138,9 @@ int prt_b200_download_wide(const prt_b200 *cc, void *nodes4_out) {
 uint64_t prt_b200_launch_count(const prt_b200 *c) { return c ? c->launches : 0; }
 float prt_b200_last_build_ms(const prt_b200 *c) { return c ? c->last_build_ms : 0.f; }
 float prt_b200_last_trace_ms(const prt_b200 *c) { return c ? c->last_trace_ms : 0.f; }
+float prt_b200_last_kernel_ms(const prt_b200 *c) { return c ? c->last_kernel_ms : 0.f; }
+uint64_t prt_b200_exotic_rays(const prt_b200 *c) { return c ? c->exotic_rays : 0; }
+uint64_t prt_b200_l2_bytes(const prt_b200 *c) { return c ? c->l2_bytes : 0; }
 
 int prt_b200_download_bvh(const prt_b200 *cc, void *nodes_out, void *tris_out) {
 	prt_b200 *c = const_cast<prt_b200 *>(cc);

@@ -87,6 +87,7 @@ struct prt_b200 {
 	static constexpr int PIPE = 4;
 	cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr; // around the traversal kernel alone (device entry points)
 	cudaEvent_t ev_pipe[PIPE][3] = {};
 	std::string name;
 	std::string err;
@@ -135,6 +136,10 @@ struct prt_b200 {
 	prt::DevBuf rays_dev[PIPE], hits_dev[PIPE], counter;
 	prt::DevBuf stack_ovf[2]; // overflow of the shared-memory traversal stacks, per launch slot
 	prt::DevBuf slow_list[2]; // rays the fast kernel set aside for the exact kernel, per launch slot
+	prt::DevBuf coop_buf[2], coop_lifo[2]; // cooperative tail (prt_trace_kernel.cuh: k_coop): handed-over rays, LIFOs
+	const void *coop_seen[2] = {nullptr, nullptr};
+	int coop_blocks = 4;      // env PRT_B200_COOP_BLOCKS: blocks per SM of the follow-up kernel
+	int coop_after = 8;       // env PRT_B200_COOP: iterations past the end of the batch before a warp goes cooperative (0 = never)
 	// the exact pass of the last EXOTIC_DEFERRED launch (trace.cu: finish_exotic)
 	bool pending_exotic = false;
 	alignas(16) unsigned char exotic_blob[384] = {}; // its TraceParams
@@ -171,6 +176,7 @@ struct prt_b200 {
 	bool pipe_trace = false; // env PRT_B200_PIPE_TRACE: print the stage timeline of every host call
 	uint64_t launches = 0;
 	float last_build_ms = 0.f, last_trace_ms = 0.f;
+	float last_kernel_ms = 0.f; // the traversal kernel of the last device-resident trace, without reordering
 	uint64_t last_h2d_bytes = 0, last_d2h_bytes = 0; // what the last host call moved over PCIe
 };
 

@@ -26,11 +26,14 @@ PRT_HD float fmul(float a, float b) { return __fmul_rn(a, b); }
 PRT_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
 PRT_HD float fsub(float a, float b) { return __fsub_rn(a, b); }
 PRT_HD float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+// 1.0f / x: the correctly rounded reciprocal IS RN(1/x), the reference's `1.0f / d` (bvh.hpp:199-201)
+PRT_HD float frcp(float x) { return __frcp_rn(x); }
 #else
 PRT_HD float fmul(float a, float b) { return a * b; }
 PRT_HD float fadd(float a, float b) { return a + b; }
 PRT_HD float fsub(float a, float b) { return a - b; }
 PRT_HD float fdiv(float a, float b) { return a / b; }
+PRT_HD float frcp(float x) { return 1.0f / x; }
 #endif
 
 // std::min / std::max of the reference: (b<a)?b:a and (a<b)?b:a.  NaN-order-sensitive, unlike
@@ -211,7 +214,7 @@ PRT_HD RayC make_ray(const float *r6) {
 	for (int a = 0; a < 3; ++a) {
 		r.o[a] = r6[a];
 		r.d[a] = r6[a + 3];
-		r.idir[a] = fdiv(1.0f, r6[a + 3]);
+		r.idir[a] = frcp(r6[a + 3]);
 	}
 	return r;
 }
@@ -250,7 +253,7 @@ PRT_HD bool moller_trumbore_ref(const RayC &r, const float *v0, const float *e1,
 	float det = fadd(fadd(fmul(e1[0], p0), fmul(e1[1], p1)), fmul(e1[2], p2));
 	if (det == 0.0f)
 		return false;
-	float inv = fdiv(1.0f, det);
+	float inv = frcp(det);
 	float s0 = fsub(r.o[0], v0[0]);
 	float s1 = fsub(r.o[1], v0[1]);
 	float s2 = fsub(r.o[2], v0[2]);
@@ -300,7 +303,7 @@ PRT_HD WoopRay make_woop_ray(const RayC &r) {
 	}
 	w.Sx = fdiv(pick3(r.d, w.kx), dz);
 	w.Sy = fdiv(pick3(r.d, w.ky), dz);
-	w.Sz = fdiv(1.0f, dz);
+	w.Sz = frcp(dz);
 	return w;
 }
 
@@ -330,7 +333,7 @@ PRT_HD bool woop_watertight(const RayC &r, const WoopRay &w, const float *a, con
 		return false;
 	const float Az = fmul(w.Sz, Akz), Bz = fmul(w.Sz, Bkz), Cz = fmul(w.Sz, Ckz);
 	const float T = fadd(fadd(fmul(U, Az), fmul(V, Bz)), fmul(W, Cz));
-	const float inv = fdiv(1.0f, det);
+	const float inv = frcp(det);
 	t = fmul(T, inv);
 	u = fmul(V, inv);
 	v = fmul(W, inv);

@@ -18,6 +18,10 @@ constexpr int SMEM_STACK = PRT_SMEM_STACK;
 #ifndef PRT_MIN_BLOCKS
 #define PRT_MIN_BLOCKS 8
 #endif
+// node steps between two votes of the warp (leaf phase? enough lanes busy?)
+#ifndef PRT_NODE_BURST
+#define PRT_NODE_BURST 2
+#endif
 
 struct TraceParams {
 	const Node *nodes;
@@ -54,14 +58,28 @@ struct TraceParams {
 	uint32_t slow_cap;
 	const unsigned long long *slow_count;      // exact kernel as second pass: how many were set aside
 	volatile unsigned long long *slow_host;    // mapped host word: count + 1 once the fast kernel is done
+	// cooperative tail (k_coop below): rays a warp is still tracing `coop_after` iterations after the
+	// end of the batch are handed over -- state and pending stack -- to a follow-up kernel that
+	// gives every such ray a whole warp (0 = never)
+	uint32_t *coop;          // [0] handed over, [1] taken, then coop_cap records of coop_rec words
+	uint32_t coop_cap;       // records available (a full list just means: keep tracing here)
+	uint32_t coop_rec;       // words per record: COOP_PARK + 2 * coop_depth
+	uint32_t coop_depth;     // stack entries a record can hold
+	uint2 *coop_lifo;        // k_coop: LIFO area, coop_lifo_cap entries per warp of its grid
+	uint32_t coop_lifo_cap;
+	int coop_after;
 };
 
+constexpr int COOP_PARK = 16; // words of a parked ray state
+
 // Per-thread stack: SMEM_STACK entries in shared memory, the rest in global memory.
-struct DevStack {
+// PF (the wide-node kernels, i.e. scenes that do not fit L2): nodes are prefetched into L2 as they
+// are pushed -- most pushed subtrees of an incoherent ray are visited later.
+template <bool PF> struct DevStack {
 	uint2 *sm;  // &block_stack[threadIdx.x], entry k at sm[k * TRACE_THREADS]
 	uint2 *ovf; // &overflow[global thread], entry k at ovf[k * stride]
 	uint32_t stride;
-	const char *pf_base; // nodes are prefetched into L2 as they are pushed (nullptr: off)
+	const char *pf_base; // PF: node array, or nullptr = off
 	int sp;
 	__device__ __forceinline__ void push(uint32_t node, uint32_t tmin_bits) {
 		if (sp < SMEM_STACK)
@@ -69,7 +87,7 @@ struct DevStack {
 		else
 			ovf[(size_t)(sp - SMEM_STACK) * stride] = make_uint2(node, tmin_bits);
 		++sp;
-		if (pf_base && (int32_t)node >= 0)
+		if (PF && pf_base && (int32_t)node >= 0)
 			asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_base + (size_t)node * 64));
 	}
 	__device__ __forceinline__ void pop(uint32_t &node, uint32_t &tmin_bits) {
@@ -77,6 +95,17 @@ struct DevStack {
 		const uint2 e = sp < SMEM_STACK ? sm[sp * TRACE_THREADS] : ovf[(size_t)(sp - SMEM_STACK) * stride];
 		node = e.x;
 		tmin_bits = e.y;
+	}
+	__device__ __forceinline__ uint2 peek(int k) const { // entry k from the bottom
+		return k < SMEM_STACK ? sm[k * TRACE_THREADS] : ovf[(size_t)(k - SMEM_STACK) * stride];
+	}
+	__device__ __forceinline__ bool room(int k) const { return sp + k <= SMEM_STACK; }
+	__device__ __forceinline__ void put(int at, bool pred, uint32_t node, uint32_t tmin_bits) {
+		if (pred) { // (a predicated store: no divergent region per entry)
+			sm[at * TRACE_THREADS] = make_uint2(node, tmin_bits);
+			if (PF && pf_base && (int32_t)node >= 0)
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_base + (size_t)node * 64));
+		}
 	}
 };
 
@@ -125,6 +154,188 @@ __device__ __forceinline__ void write_hit(const TraceParams &P, uint64_t i, cons
 	}
 }
 
+// Cooperative tail.  When the batch is exhausted, a kernel's remaining time is the latency of its
+// longest rays: a lone lane advances one tree element per ~500 cycles of dependent instructions,
+// and a ray through a vertex shared by a fan of 186 triangles needs hundreds of them while the
+// other 31 lanes -- and soon the whole GPU -- idle (measured on C2: 0.18 ms of a 0.37 ms launch,
+// whatever the batch size).  A warp that is still busy `coop_after` iterations after the end of
+// the batch therefore hands its unfinished rays over (state + pending stack, one record each) and
+// leaves; k_coop, launched right behind, finishes every such ray WITH ALL 32 LANES OF A WARP: the
+// ray's pending subtrees become a LIFO; every round each lane takes one entry off the top, tests
+// the two children of a node or the triangle of a leaf, and the surviving children are appended
+// with ballot-derived positions; the pruning limit is shared by a warp minimum whenever a lane
+// finds a closer hit, and the lanes' best hits are merged at the end.  The result is the minimum
+// over all accepted triangles under the order-independent tie rule (lowest primitive id), exactly
+// as in the sequential traversal -- the visit order differs, nothing else.  LIFO size: a round
+// removes <= 32 entries and adds <= 64 one level deeper, so it holds at most 32 entries per level.
+// The last <= 64 entries pushed also sit in a shared-memory window, so a round whose entries were
+// all pushed by the round before never waits for L2.
+constexpr int COOP_THREADS = 128;
+
+template <uint32_t MASK, bool AOS, bool WT>
+__global__ void __launch_bounds__(COOP_THREADS) k_coop(const TraceParams P) {
+	constexpr bool ANYHIT = (MASK == PRT_TAG_VALID);
+	constexpr bool WANT_UV = (MASK & PRT_TAG_UV) != 0;
+	constexpr bool TRACK_PRIM = (MASK & (PRT_TAG_UV | PRT_TAG_PID)) != 0;
+	__shared__ uint2 s_xb[64 * (COOP_THREADS / 32)];
+	__shared__ float s_idir[3 * COOP_THREADS];
+	const unsigned lane = threadIdx.x & 31;
+	const unsigned lt = (1u << lane) - 1u;
+	uint2 *xb = s_xb + 64 * (threadIdx.x >> 5);
+	const uint32_t handed = min(P.coop[0], P.coop_cap);
+	const size_t warp_global = ((size_t)blockIdx.x * COOP_THREADS + threadIdx.x) >> 5;
+	uint2 *q = P.coop_lifo + warp_global * P.coop_lifo_cap;
+	TraverseOpts opts;
+	opts.prune = P.prune;
+	opts.slack_rel = P.slack_rel;
+	opts.slack_ulps = P.slack_ulps;
+	TravState s;
+	RayC r;
+	FastRay fr;
+	WoopRay wr{};
+	for (;;) {
+		uint32_t w = 0;
+		if (lane == 0)
+			w = atomicAdd(P.coop + 1, 1u);
+		w = __shfl_sync(0xffffffffu, w, 0);
+		if (w >= handed)
+			break;
+		const uint32_t *p = P.coop + 4 + (size_t)w * P.coop_rec;
+		const uint64_t ray_b = (uint64_t)__ldcg(p) | ((uint64_t)__ldcg(p + 1) << 32);
+		float r6[6];
+#pragma unroll
+		for (int k = 0; k < 6; ++k)
+			r6[k] = u2f(__ldcg(p + 2 + k));
+		r = make_ray(r6);
+		fr = make_fast_ray(r, P.scene_absmax, false);
+		if (WT)
+			wr = make_woop_ray(r);
+		trav_init(s, r, opts, P.n_tris, P.root);
+		s.t_best = u2f(__ldcg(p + 8));
+		s.u_best = u2f(__ldcg(p + 9));
+		s.v_best = u2f(__ldcg(p + 10));
+		s.prim_best = __ldcg(p + 11);
+		if (opts.prune && s.t_best < INFINITY)
+			s.limit = fadd(s.t_best, fadd(fmul(fabsf(s.t_best), opts.slack_rel), s.slack_abs));
+		const int32_t cur_b = (int32_t)__ldcg(p + 12);
+		const uint32_t sp_b = __ldcg(p + 13);
+#pragma unroll
+		for (int a = 0; a < 3; ++a)
+			s_idir[a * COOP_THREADS + threadIdx.x] = r.idir[a];
+		// seed the LIFO: the ray's stack, bottom first, then its current element on top
+		const uint2 *st = reinterpret_cast<const uint2 *>(p + COOP_PARK);
+		for (uint32_t k = lane; k < sp_b; k += 32)
+			__stcg(q + k, __ldcg(st + k));
+		uint32_t qn = sp_b + 1u;
+		if (lane == 0) {
+			const uint2 top = make_uint2((uint32_t)cur_b, 0xff800000u /* entry distance -inf */);
+			__stcg(q + sp_b, top);
+			xb[0] = top;
+		}
+		uint32_t xb_base = sp_b, xb_cnt = 1; // window of the entries pushed last
+		__syncwarp();
+		bool done = false;
+		while (qn > 0 && !done) {
+			const uint32_t take = qn < 32u ? qn : 32u;
+			int32_t item = PRT_DONE;
+			if (lane < take) {
+				const uint32_t at = qn - 1 - lane;
+				const uint2 e = (at >= xb_base && at < xb_base + xb_cnt) ? xb[at - xb_base] : __ldcg(q + at);
+				if (!(u2f(e.y) > s.limit))
+					item = (int32_t)e.x;
+			}
+			qn -= take;
+			int32_t c0 = PRT_DONE, c1 = PRT_DONE;
+			float tm0 = 0.f, tm1 = 0.f;
+			bool found = false;
+			if (at_node(item)) {
+				const char *np = reinterpret_cast<const char *>(P.nodes + item);
+				Vec4 a, bb, c, d;
+				ld32(np, a, bb);
+				ld32(np + 32, c, d);
+				const float lo0[3] = {a.x, a.y, a.z}, hi0[3] = {a.w, bb.x, bb.y};
+				const float lo1[3] = {bb.z, bb.w, c.x}, hi1[3] = {c.y, c.z, c.w};
+				if (slab_fast(fr, lo0, hi0, s.limit, tm0))
+					c0 = (int32_t)f2u(d.x);
+				if (slab_fast(fr, lo1, hi1, s.limit, tm1))
+					c1 = (int32_t)f2u(d.y);
+				if (c0 != PRT_DONE && c1 != PRT_DONE && tm0 < tm1) { // nearer child on top
+					const int32_t ti = c0;
+					c0 = c1;
+					c1 = ti;
+					const float tf = tm0;
+					tm0 = tm1;
+					tm1 = tf;
+				}
+			} else if (item < 0) {
+				const float before = s.limit;
+				trav_leaf_test<ANYHIT, WANT_UV, TRACK_PRIM, false, true, WT>(
+				    s, item, P.tris, r, opts, &wr, s_idir + threadIdx.x, COOP_THREADS);
+				found = s.limit < before;
+			}
+			if (ANYHIT)
+				done = __any_sync(0xffffffffu, s.t_best < INFINITY);
+			if (__any_sync(0xffffffffu, found)) { // share the pruning limit
+				float l = s.limit;
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1)
+					l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o));
+				s.limit = l;
+			}
+			const unsigned m0 = __ballot_sync(0xffffffffu, c0 != PRT_DONE);
+			const unsigned m1 = __ballot_sync(0xffffffffu, c1 != PRT_DONE);
+			const uint32_t n0 = __popc(m0), n1 = __popc(m1);
+			if (qn + n0 + n1 > P.coop_lifo_cap)
+				__trap(); // cannot happen (see the bound above); never corrupt memory silently
+			if (c0 != PRT_DONE) {
+				const uint32_t k = __popc(m0 & lt);
+				const uint2 e = make_uint2((uint32_t)c0, f2u(tm0));
+				xb[k] = e;
+				__stcg(q + qn + k, e);
+			}
+			if (c1 != PRT_DONE) {
+				const uint32_t k = n0 + __popc(m1 & lt);
+				const uint2 e = make_uint2((uint32_t)c1, f2u(tm1));
+				xb[k] = e;
+				__stcg(q + qn + k, e);
+			}
+			xb_base = qn;
+			xb_cnt = n0 + n1;
+			qn += n0 + n1;
+			__syncwarp();
+		}
+		// merge the lanes' best hits (same order-independent rule as everywhere else)
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			const float ot = __shfl_xor_sync(0xffffffffu, s.t_best, o);
+			const uint32_t op = __shfl_xor_sync(0xffffffffu, s.prim_best, o);
+			const float ou = __shfl_xor_sync(0xffffffffu, s.u_best, o);
+			const float ov = __shfl_xor_sync(0xffffffffu, s.v_best, o);
+			const bool take = TRACK_PRIM ? closer(ot, op, s.t_best, s.prim_best) : (ot < s.t_best);
+			if (take) {
+				s.t_best = ot;
+				s.prim_best = op;
+				s.u_best = ou;
+				s.v_best = ov;
+			}
+		}
+		if (lane == 0)
+			write_hit<MASK, AOS, false>(P, ray_b, r, s);
+		__syncwarp();
+	}
+	// the last warp to leave re-arms the list for the next launch
+	if (lane == 0) {
+		const unsigned warps = gridDim.x * (COOP_THREADS / 32);
+		__threadfence();
+		if (atomicAdd(P.coop + 2, 1u) == warps - 1) {
+			__threadfence();
+			P.coop[0] = 0;
+			P.coop[1] = 0;
+			P.coop[2] = 0;
+		}
+	}
+}
+
 // Persistent warps, one ray per lane, with three measures against SIMT divergence:
 //   * dynamic ray fetch: finished lanes write their record and, as soon as fewer than `refill`
 //     lanes of the warp are still traversing, all idle lanes pull new rays from the global counter
@@ -149,7 +360,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, PRT_MIN_BLOCKS) k_trace(const T
 	constexpr bool TRACK_PRIM = (MASK & (PRT_TAG_UV | PRT_TAG_PID)) != 0;
 	constexpr bool FAST = !EXACT;
 	constexpr bool W = WIDE && FAST;
+	constexpr bool COOP = FAST && !W && !COUNT; // the cooperative tail serves the binary fast kernels
 	__shared__ uint2 s_stack[SMEM_STACK * TRACE_THREADS];
+	__shared__ float s_idir[FAST ? 3 * TRACE_THREADS : 1]; // 1.0f / d of the lane's ray (fast kernels)
 
 	const unsigned lane = threadIdx.x & 31;
 	const unsigned lt = (1u << lane) - 1u;
@@ -170,14 +383,14 @@ __global__ void __launch_bounds__(TRACE_THREADS, PRT_MIN_BLOCKS) k_trace(const T
 		} // else: the list overflowed, every ray is traced again (same results)
 	}
 
-	DevStack stack;
+	DevStack<W> stack;
 	stack.sm = s_stack + threadIdx.x;
 	stack.ovf = P.stack_ovf + ((size_t)blockIdx.x * TRACE_THREADS + threadIdx.x);
 	stack.stride = P.ovf_stride;
-	stack.pf_base = P.prefetch ? (W ? reinterpret_cast<const char *>(P.nodes4)
-	                                : reinterpret_cast<const char *>(P.nodes))
-	                           : nullptr;
+	stack.pf_base = (W && P.prefetch) ? reinterpret_cast<const char *>(P.nodes4) : nullptr;
 	stack.sp = 0;
+	const float *my_idir = FAST ? s_idir + threadIdx.x : nullptr; // (the exact kernels do not need it)
+	constexpr int idir_stride = TRACE_THREADS;
 	TravState s;
 	RayC r;
 	FastRay fr;
@@ -185,6 +398,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PRT_MIN_BLOCKS) k_trace(const T
 	uint64_t ray = 0;
 	bool has_ray = false;
 	bool exhausted = false; // warp-uniform: the global counter ran past the last ray
+	int tail_iters = 0;     // warp-uniform: iterations since then
 	s.cur = PRT_DONE;
 
 	for (;;) {
@@ -230,6 +444,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, PRT_MIN_BLOCKS) k_trace(const T
 						}
 					}
 					if (mine) {
+						if (FAST) {
+#pragma unroll
+							for (int a = 0; a < 3; ++a)
+								s_idir[a * TRACE_THREADS + threadIdx.x] = r.idir[a];
+						}
 						if (WT)
 							wr = make_woop_ray(r);
 						trav_init(s, r, opts, P.n_tris, P.root);
@@ -248,23 +467,56 @@ __global__ void __launch_bounds__(TRACE_THREADS, PRT_MIN_BLOCKS) k_trace(const T
 
 		// ---- traverse until too few lanes are still busy
 		for (;;) {
-			if (has_ray && at_node(s.cur)) {
-				trav_node_step<COUNT, FAST, W, WT>(s, stack, P.nodes, P.nodes4, r, fr);
-				if (s.cur < 0) // parked at a triangle: have its record on the way
-					asm volatile("prefetch.global.L1 [%0];" ::"l"(P.tris + (uint32_t)(~s.cur)));
+#pragma unroll
+			for (int k = 0; k < PRT_NODE_BURST; ++k) {
+				if (has_ray && at_node(s.cur)) {
+					trav_node_step<COUNT, FAST, W, WT>(s, stack, P.nodes, P.nodes4, r, fr);
+					if (s.cur < 0) // parked at a triangle: have its record on the way
+						asm volatile("prefetch.global.L1 [%0];" ::"l"(P.tris + (uint32_t)(~s.cur)));
+				}
 			}
 			const bool leaf = has_ray && s.cur < 0;
 			const unsigned leafm = __ballot_sync(0xffffffffu, leaf);
 			const unsigned nodem = __ballot_sync(0xffffffffu, has_ray && at_node(s.cur));
-			if (leafm && (nodem == 0 ||
-			              __popc(leafm) * 32 >= P.leaf_votes * (__popc(leafm) + __popc(nodem)))) {
-				if (leaf)
-					trav_leaf_step<ANYHIT, WANT_UV, TRACK_PRIM, COUNT, FAST, WT>(s, stack, P.tris, r,
-					                                                             opts, &wr);
+			const int busy = __popc(leafm | nodem);
+			if (busy == 0 || (!exhausted && busy < P.refill))
+				break; // (lanes parked at a triangle stay parked across the refill)
+			// still busy long after the end of the batch: hand the unfinished rays over to k_coop
+			if (COOP && exhausted && P.coop_after > 0 && ++tail_iters > P.coop_after) {
+				if (leaf || (has_ray && at_node(s.cur))) {
+					const uint32_t at = atomicAdd(P.coop, 1u);
+					if (at < P.coop_cap && (uint32_t)stack.sp <= P.coop_depth) {
+						uint32_t *p = P.coop + 4 + (size_t)at * P.coop_rec;
+						__stcg(p + 0, (uint32_t)ray);
+						__stcg(p + 1, (uint32_t)(ray >> 32));
+#pragma unroll
+						for (int a = 0; a < 3; ++a) {
+							__stcg(p + 2 + a, f2u(r.o[a]));
+							__stcg(p + 5 + a, f2u(r.d[a]));
+						}
+						__stcg(p + 8, f2u(s.t_best));
+						__stcg(p + 9, f2u(s.u_best));
+						__stcg(p + 10, f2u(s.v_best));
+						__stcg(p + 11, s.prim_best);
+						__stcg(p + 12, (uint32_t)s.cur);
+						__stcg(p + 13, (uint32_t)stack.sp);
+						uint2 *st = reinterpret_cast<uint2 *>(p + COOP_PARK);
+						for (int k = 0; k < stack.sp; ++k)
+							__stcg(st + k, stack.peek(k));
+						has_ray = false; // (its record is written by k_coop)
+						s.cur = PRT_DONE;
+					} // else: the list is full -- this lane keeps tracing here
+				}
+				tail_iters = 0; // lanes that could not be handed over try again later
+				continue;
 			}
-			const unsigned busy = __ballot_sync(0xffffffffu, has_ray && s.cur != PRT_DONE);
-			if (busy == 0 || (!exhausted && __popc(busy) < P.refill))
-				break;
+			// (once the batch is exhausted nobody waits: what is left is the tail of the kernel,
+			// bound by the latency of its longest rays)
+			if (leafm && (nodem == 0 || exhausted || __popc(leafm) * 32 >= P.leaf_votes * busy)) {
+				if (leaf)
+					trav_leaf_step<ANYHIT, WANT_UV, TRACK_PRIM, COUNT, FAST, WT>(
+					    s, stack, P.tris, r, opts, &wr, my_idir, idir_stride);
+			}
 		}
 	}
 	// The last warp to leave re-arms the counters for the next launch (no cudaMemset between
@@ -320,5 +572,6 @@ KernelFn trace_kernel_exact(uint32_t mask, bool aos);    // trace_exact.cu
 KernelFn trace_kernel_wt(uint32_t mask, bool aos);       // trace_wt.cu
 KernelFn trace_kernel_wt_exact(uint32_t mask, bool aos); // trace_wt.cu
 KernelFn trace_kernel_count(bool wide, bool wt);         // trace_exact.cu (instrumented runs)
+KernelFn coop_kernel(uint32_t mask, bool aos, bool wt);  // trace_coop.cu
 
 } // namespace prt

@@ -30,12 +30,23 @@ __device__ __forceinline__ Vec4 ld16(const void *p) {
 	const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
 	return Vec4{v.x, v.y, v.z, v.w};
 }
+// 32 bytes with ONE instruction: sm_100 has 256-bit global loads (LDG.E.ENL2.256); a 64-byte node
+// or triangle record is two L1 lookups instead of four
+__device__ __forceinline__ void ld32(const void *p, Vec4 &a, Vec4 &b) {
+	asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+	             : "l"(p));
+}
 __device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
 __device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
 #else
 inline Vec4 ld16(const void *p) {
 	const float *f = static_cast<const float *>(p);
 	return Vec4{f[0], f[1], f[2], f[3]};
+}
+inline void ld32(const void *p, Vec4 &a, Vec4 &b) {
+	a = ld16(p);
+	b = ld16(static_cast<const char *>(p) + 16);
 }
 inline uint32_t f2u(float f) {
 	uint32_t u;
@@ -75,6 +86,15 @@ struct ArrayStack {
 		--sp;
 		node = e[sp].node;
 		tmin_bits = e[sp].tmin_bits;
+	}
+	// several conditional pushes without a branch per entry: room(k) says that k more entries can
+	// be placed with put() at absolute positions (the device stack: inside its shared-memory part)
+	PRT_HD bool room(int) const { return true; }
+	PRT_HD void put(int at, bool pred, uint32_t node, uint32_t tmin_bits) {
+		if (pred) {
+			e[at].node = node;
+			e[at].tmin_bits = tmin_bits;
+		}
 	}
 };
 
@@ -231,7 +251,9 @@ template <class STK> PRT_HD void trav_pop(TravState &s, STK &stack) {
 template <class STK>
 PRT_HD bool wide_node_step(TravState &s, STK &stack, const Node4 *nodes4, const FastRay &fr) {
 	const char *np = reinterpret_cast<const char *>(nodes4 + s.cur);
-	const Vec4 v0 = ld16(np), v1 = ld16(np + 16), v2 = ld16(np + 32), v3 = ld16(np + 48);
+	Vec4 v0, v1, v2, v3;
+	ld32(np, v0, v1);
+	ld32(np + 32, v2, v3);
 	const uint32_t ebits = f2u(v0.w);
 	const uint32_t qw[6] = {f2u(v1.x), f2u(v1.y), f2u(v1.z), f2u(v1.w), f2u(v2.x), f2u(v2.y)};
 	const int32_t ch[4] = {(int32_t)f2u(v2.z), (int32_t)f2u(v2.w), (int32_t)f2u(v3.x),
@@ -285,10 +307,18 @@ PRT_HD bool wide_node_step(TravState &s, STK &stack, const Node4 *nodes4, const 
 	PRT_CSWAP(1, 3)
 	PRT_CSWAP(1, 2)
 #undef PRT_CSWAP
+	// push the others farthest first: child k (1 <= k < nh) lands at sp + nh - 1 - k
+	if (stack.room(3)) {
 #pragma unroll
-	for (int k = 3; k >= 1; --k)
-		if (k < nh)
-			stack.push((uint32_t)c[k], f2u(t[k]));
+		for (int k = 3; k >= 1; --k)
+			stack.put(stack.sp + nh - 1 - k, k < nh, (uint32_t)c[k], f2u(t[k]));
+		stack.sp += nh - 1;
+	} else {
+#pragma unroll
+		for (int k = 3; k >= 1; --k)
+			if (k < nh)
+				stack.push((uint32_t)c[k], f2u(t[k]));
+	}
 	s.cur = c[0];
 	return false;
 }
@@ -306,7 +336,9 @@ PRT_HD void trav_node_step(TravState &s, STK &stack, const Node *nodes, const No
 		pop = wide_node_step(s, stack, nodes4, fr);
 	} else {
 		const char *np = reinterpret_cast<const char *>(nodes + s.cur);
-		const Vec4 a = ld16(np), b = ld16(np + 16), c = ld16(np + 32), d = ld16(np + 48);
+		Vec4 a, b, c, d;
+		ld32(np, a, b);
+		ld32(np + 32, c, d);
 		const int32_t c0 = (int32_t)f2u(d.x), c1 = (int32_t)f2u(d.y);
 		const float lo0[3] = {a.x, a.y, a.z}, hi0[3] = {a.w, b.x, b.y};
 		const float lo1[3] = {b.z, b.w, c.x}, hi1[3] = {c.y, c.z, c.w};
@@ -342,11 +374,18 @@ PRT_HD void trav_node_step(TravState &s, STK &stack, const Node *nodes, const No
 // very box.  WT = opt-in watertight mode (prt_math.cuh: woop_watertight): the records carry the
 // original vertices (v1, v2 in place of the edges) and the triangle's own box keeps only the
 // reference's domain rule, conservatively.
-template <bool ANYHIT, bool WANT_UV, bool TRACK_PRIM, bool COUNT, bool FAST, bool WT, class STK>
-PRT_HD void trav_leaf_step(TravState &s, STK &stack, const TriRec *tris, const RayC &r,
-                           const TraverseOpts &opt, const WoopRay *wr) {
-	const char *tp = reinterpret_cast<const char *>(tris + (uint32_t)(~s.cur));
-	const Vec4 q0 = ld16(tp), q1 = ld16(tp + 16), q2 = ld16(tp + 32);
+// idir / idir_stride: where the ray's 1.0f / d lives (the fast kernels park it in shared memory: it
+// is needed about once per ray, for the exact verdict on a triangle's own box).
+// trav_leaf_test: the triangle `leaf` (~record index) against the ray; updates the best hit and the
+// pruning limit; returns true when the ray is finished (any-hit queries).
+template <bool ANYHIT, bool WANT_UV, bool TRACK_PRIM, bool COUNT, bool FAST, bool WT>
+PRT_HD bool trav_leaf_test(TravState &s, int32_t leaf, const TriRec *tris, const RayC &r,
+                           const TraverseOpts &opt, const WoopRay *wr, const float *idir,
+                           int idir_stride) {
+	const char *tp = reinterpret_cast<const char *>(tris + (uint32_t)(~leaf));
+	Vec4 q0, q1, q2, q3;
+	ld32(tp, q0, q1);
+	ld32(tp + 32, q2, q3);
 	if (COUNT)
 		++s.n_tris;
 	const float v0[3] = {q0.x, q0.y, q0.z};
@@ -361,28 +400,21 @@ PRT_HD void trav_leaf_step(TravState &s, STK &stack, const TriRec *tris, const R
 		                                         : (t < s.t_best));
 		bool box_ok = true;
 		if (FAST && better) {
-			const Vec4 q3 = ld16(tp + 48);
 			const float lo[3] = {q1.w, q2.w, q3.x}, hi[3] = {q3.y, q3.z, q3.w};
-			// 1.0f / d is recomputed here (about once per ray) instead of being carried through the
-			// whole traversal: the fast test works on its own slopes and intercepts
 			RayC rr;
 #pragma unroll
 			for (int a = 0; a < 3; ++a) {
 				rr.o[a] = r.o[a];
 				rr.d[a] = r.d[a];
-				rr.idir[a] = fdiv(1.0f, r.d[a]);
+				rr.idir[a] = idir[a * idir_stride];
 			}
 			float tm;
 			box_ok = WT ? slab_cons(rr, lo, hi, tm) : slab_ref(rr, lo, hi, tm);
 		}
 		if (better && box_ok) {
 			s.t_best = t;
-			if (ANYHIT) {
-				// `valid` is t_near < inf (bvh.hpp:260): any candidate with t < inf decides it
-				// (a NaN or +inf t never updates t_near, bvh.hpp:247)
-				s.cur = PRT_DONE;
-				return;
-			}
+			if (ANYHIT) // `valid` is t_near < inf (bvh.hpp:260): any candidate with t < inf decides it
+				return true; // (a NaN or +inf t never updates t_near, bvh.hpp:247)
 			s.prim_best = prim;
 			if (WANT_UV) {
 				s.u_best = u;
@@ -392,7 +424,18 @@ PRT_HD void trav_leaf_step(TravState &s, STK &stack, const TriRec *tris, const R
 				s.limit = fadd(t, fadd(fmul(fabsf(t), opt.slack_rel), s.slack_abs));
 		}
 	}
-	trav_pop(s, stack);
+	return false;
+}
+
+template <bool ANYHIT, bool WANT_UV, bool TRACK_PRIM, bool COUNT, bool FAST, bool WT, class STK>
+PRT_HD void trav_leaf_step(TravState &s, STK &stack, const TriRec *tris, const RayC &r,
+                           const TraverseOpts &opt, const WoopRay *wr, const float *idir,
+                           int idir_stride) {
+	if (trav_leaf_test<ANYHIT, WANT_UV, TRACK_PRIM, COUNT, FAST, WT>(s, s.cur, tris, r, opt, wr, idir,
+	                                                                idir_stride))
+		s.cur = PRT_DONE;
+	else
+		trav_pop(s, stack);
 }
 
 // Scalar driver (instrumented kernel and the host-side emulator): one ray start to finish.
@@ -411,7 +454,8 @@ PRT_HD void traverse(const Node *nodes, const TriRec *tris, uint64_t n_tris_scen
 		if (s.cur >= 0)
 			trav_node_step<COUNT, FAST, WIDE, WT>(s, stack, nodes, nodes4, r, fr);
 		else
-			trav_leaf_step<ANYHIT, WANT_UV, TRACK_PRIM, COUNT, FAST, WT>(s, stack, tris, r, opt, &wr);
+			trav_leaf_step<ANYHIT, WANT_UV, TRACK_PRIM, COUNT, FAST, WT>(s, stack, tris, r, opt, &wr,
+			                                                             r.idir, 1);
 	}
 	out.t = s.t_best;
 	out.u = s.u_best;

@@ -173,7 +173,8 @@ static int stack_bound(const prt_b200 *c, bool wide) {
 }
 
 static int launch_kernel(prt_b200 *c, KernelFn fn, int cache_slot, uint32_t mask, TraceParams &P,
-                         uint64_t n, bool wide, int slot, cudaStream_t s) {
+                         uint64_t n, bool wide, int slot, cudaStream_t s, bool timed = false,
+                         bool coop = false) {
 	int bps = cache_slot >= 0 ? c->bps_cache[mask][cache_slot] : 0;
 	if (bps == 0) {
 		PRT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, TRACE_THREADS, 0));
@@ -190,8 +191,43 @@ static int launch_kernel(prt_b200 *c, KernelFn fn, int cache_slot, uint32_t mask
 	PRT_CUDA(c, c->stack_ovf[slot].reserve(threads * (uint64_t)deep * sizeof(uint2)));
 	P.stack_ovf = c->stack_ovf[slot].as<uint2>();
 	P.ovf_stride = (uint32_t)threads;
+	// cooperative tail of the binary fast kernels: a list of handed-over rays (state + stack) and,
+	// for the follow-up kernel, a LIFO of 32 entries per tree level for each of its warps
+	P.coop = nullptr;
+	P.coop_cap = 0;
+	P.coop_after = 0;
+	const bool use_coop = coop && c->coop_after > 0;
+	constexpr uint32_t COOP_CAP = 8192;
+	const int coop_grid = c->sm_count * c->coop_blocks;
+	if (use_coop) {
+		const uint32_t depth = (uint32_t)stack_bound(c, false) + 1;
+		const uint32_t rec = COOP_PARK + 2 * depth;
+		const bool fresh = c->coop_buf[slot].p == nullptr;
+		PRT_CUDA(c, c->coop_buf[slot].reserve((4 + (uint64_t)COOP_CAP * rec) * 4));
+		if (fresh || c->coop_buf[slot].p != c->coop_seen[slot]) { // (re)allocated: arm the counters
+			PRT_CUDA(c, cudaMemsetAsync(c->coop_buf[slot].p, 0, 16, s));
+			c->coop_seen[slot] = c->coop_buf[slot].p;
+		}
+		const uint32_t lifo_cap = 32 * (depth + 3);
+		PRT_CUDA(c, c->coop_lifo[slot].reserve((uint64_t)coop_grid * (COOP_THREADS / 32) * lifo_cap * 8));
+		P.coop = c->coop_buf[slot].as<uint32_t>();
+		P.coop_cap = COOP_CAP;
+		P.coop_rec = rec;
+		P.coop_depth = depth;
+		P.coop_lifo = c->coop_lifo[slot].as<uint2>();
+		P.coop_lifo_cap = lifo_cap;
+		P.coop_after = c->coop_after;
+	}
+	if (timed)
+		PRT_CUDA(c, cudaEventRecord(c->ev_k0, s));
 	fn<<<(unsigned)grid, TRACE_THREADS, 0, s>>>(P);
 	c->launches += 1;
+	if (use_coop) { // finishes the rays the kernel above handed over (none: its warps leave at once)
+		coop_kernel(mask, P.aos != nullptr, c->recs_vertex_form)<<<coop_grid, COOP_THREADS, 0, s>>>(P);
+		c->launches += 1;
+	}
+	if (timed)
+		PRT_CUDA(c, cudaEventRecord(c->ev_k1, s));
 	PRT_CUDA(c, cudaGetLastError());
 	return PRT_OK;
 }
@@ -304,7 +340,8 @@ int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, c
 	if (d_counts) { // instrumented run: set-aside rays (if any) count as zero
 		PRT_CUDA(c, cudaMemsetAsync(d_counts, 0, n * 8, s));
 		P.slow_cap = 0;
-		if (int rc = launch_kernel(c, trace_kernel_count(wide, wt), -1, mask, P, n, wide, out.slot, s))
+		if (int rc = launch_kernel(c, trace_kernel_count(wide, wt), -1, mask, P, n, wide, out.slot, s,
+		                           exotic_mode == EXOTIC_DEFERRED))
 			return rc;
 		// its set-aside counter is not consumed by an exact pass: re-arm it
 		PRT_CUDA(c, cudaMemsetAsync(P.counter + 3, 0, 8, s));
@@ -312,7 +349,8 @@ int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, c
 	}
 	if (!c->fast_boxes) // the reference's box arithmetic everywhere
 		return launch_kernel(c, wt ? trace_kernel_wt_exact(mask, aos) : trace_kernel_exact(mask, aos),
-		                     (wt ? 6 : 4) + (aos ? 1 : 0), mask, P, n, false, out.slot, s);
+		                     (wt ? 6 : 4) + (aos ? 1 : 0), mask, P, n, false, out.slot, s,
+		                     exotic_mode == EXOTIC_DEFERRED);
 
 	// ---- fast kernel; the rays it cannot take go to a list
 	const uint64_t cap = n < (1ull << 32) ? std::min<uint64_t>(n, 1ull << 20) : 0;
@@ -329,7 +367,7 @@ int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, c
 	KernelFn fn = wt ? trace_kernel_wt(mask, aos)
 	                 : (wide ? trace_kernel_wide(mask, aos) : trace_kernel_fast(mask, aos));
 	if (int rc = launch_kernel(c, fn, (aos ? 1 : 0) + ((wt || wide) ? 2 : 0), mask, P, n, wide,
-	                           out.slot, s))
+	                           out.slot, s, exotic_mode == EXOTIC_DEFERRED, !wide))
 		return rc;
 	// ---- exact pass over the set-aside rays
 	P.slow_count = P.counter + 3;

@@ -216,6 +216,27 @@ def incoherent_rays(n, lo, hi, seed=4):
     return rays
 
 
+RAY_BLOCK = 1 << 20
+
+
+def incoherent_rays_range(first, count, lo, hi, seed=4):
+    """Rays [first, first+count) of an unbounded incoherent batch (config C4: 100 M rays): every
+    block of 2^20 rays has its own generator MT19937(seed * 1000003 + block), so any contiguous
+    slice -- one rank's share of a strong-scaled batch -- is produced without generating the
+    rays in front of it, and is identical to the same rows of the whole batch."""
+    out = np.empty((count, 6), F)
+    at = first
+    end = first + count
+    while at < end:
+        b = at // RAY_BLOCK
+        blk = incoherent_rays(RAY_BLOCK, lo, hi, seed=seed * 1000003 + b)
+        a0 = at - b * RAY_BLOCK
+        n = min(end - at, RAY_BLOCK - a0)
+        out[at - first: at - first + n] = blk[a0: a0 + n]
+        at += n
+    return out
+
+
 def _hash_u01(idx, salt):
     """Counter-based per-ray uniform in [0,1): a 32-bit integer hash of (ray index, salt)."""
     x = (idx.astype(np.uint64) * np.uint64(0x9E3779B1) + np.uint64(salt)) & np.uint64(0xFFFFFFFF)
