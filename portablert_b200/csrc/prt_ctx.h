@@ -168,7 +168,8 @@ struct prt_b200 {
 	int watertight = 0;                      // env PRT_B200_WATERTIGHT / prt_b200_set_triangle_test: takes effect at set_tris
 	bool recs_vertex_form = false;           // the current triangle records hold v1, v2 (watertight) instead of the edges
 	int fast_boxes = 1;                      // env PRT_B200_FAST_BOXES=0 forces the exact test everywhere
-	int refill = 16;                         // env PRT_B200_REFILL: dynamic ray-fetch threshold (lanes)
+	int refill = 16;                         // env PRT_B200_REFILL: dynamic ray-fetch threshold (lanes), binary-node kernels
+	int refill_wide = 24;                    // env PRT_B200_REFILL_WIDE: ... of the wide-node kernels (incoherent rays: measured +3.5 %)
 	int leaf_votes = 8;                      // env PRT_B200_LEAF_VOTES: lanes waiting at a triangle that start a leaf phase
 	int prefetch = 2;                        // env PRT_B200_PREFETCH: 0 never, 1 always, 2 when the BVH exceeds L2
 	bool packed_d2h = true;                  // env PRT_B200_PACKED_D2H: pageable results come back tightly packed
@@ -230,6 +231,8 @@ int host_ray_probe(const prt_b200 *c, const float *rays6, uint64_t n);
 // sort.cu
 int radix_sort_pairs(prt_b200 *c, DevBuf &scratch, uint64_t *const keys[2], uint32_t *const vals[2],
                      uint64_t n, int key_bits, cudaStream_t s, int *result_index);
+int radix_sort_pairs32(prt_b200 *c, DevBuf &scratch, uint32_t *const keys[2], uint32_t *const vals[2],
+                       uint64_t n, int key_bits, cudaStream_t s, int *result_index);
 
 int launch_read_probe(prt_b200 *c, const void *buf, uint64_t bytes, int iters, float *ms);
 

@@ -4,7 +4,9 @@
 // backend.hpp:75-83).  DMA needs page-locked memory, so such buffers are staged through a pinned
 // ring; one core copies ~10 GB/s, a PCIe 5 x16 link moves ~55 GB/s, hence several threads.  The
 // pool is created once per context (no thread creation on the call path) and runs one parallel
-// loop at a time.
+// loop at a time.  (Measured on the B200 host, 30 M rays in, 30 M 16-byte records out: 104 / 74 /
+// 39 / 33 / 32 ms with 1 / 2 / 4 / 8 / 16 copy threads -- bound by the host's memory bandwidth from
+// 8 threads on; hand-written MOVNTDQ copies were 1.4-2.5x SLOWER than glibc's memcpy there.)
 #pragma once
 
 #include <condition_variable>

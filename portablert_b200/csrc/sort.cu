@@ -1,4 +1,4 @@
-// sort.cu -- LSD radix sort of (u64 key, u32 value) pairs, 8-bit digits, one kernel per pass.
+// sort.cu -- LSD radix sort of (u64 or u32 key, u32 value) pairs, 8-bit digits, one kernel per pass.
 //
 // Used by the LBVH build (Morton keys -> triangle order) and by the ray reordering in front of the
 // traversal.  "Onesweep" organisation: one read of the keys produces the digit histograms of ALL
@@ -27,8 +27,9 @@ constexpr unsigned long long ST_PREFIX = 2ull << 62; // inclusive prefix over ti
 constexpr unsigned long long ST_MASK = (1ull << 62) - 1;
 
 // ---- all passes' digit histograms in one read of the keys ---------------------------------------
+template <class K>
 __global__ void __launch_bounds__(SO_THREADS)
-    k_sweep_hist(const uint64_t *__restrict__ keys, uint64_t n, int passes,
+    k_sweep_hist(const K *__restrict__ keys, uint64_t n, int passes,
                  uint32_t *__restrict__ ghist /* [passes][256] */) {
 	__shared__ uint32_t sh[SO_MAX_PASSES][SO_RADIX];
 	for (int p = 0; p < passes; ++p)
@@ -36,7 +37,7 @@ __global__ void __launch_bounds__(SO_THREADS)
 	__syncthreads();
 	const uint64_t stride = (uint64_t)gridDim.x * SO_THREADS;
 	for (uint64_t i = (uint64_t)blockIdx.x * SO_THREADS + threadIdx.x; i < n; i += stride) {
-		const uint64_t k = keys[i];
+		const K k = keys[i];
 		const unsigned act = __activemask();
 		for (int p = 0; p < passes; ++p) {
 			// a digit that is constant across the warp (e.g. unused high bits) would serialise
@@ -91,12 +92,13 @@ __device__ __forceinline__ uint32_t block_exscan256(uint32_t v, uint32_t *ws) {
 }
 
 // ---- one pass --------------------------------------------------------------------------------
+template <class K>
 __global__ void __launch_bounds__(SO_THREADS)
-    k_sweep_pass(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                 uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint64_t n,
+    k_sweep_pass(const K *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                 K *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint64_t n,
                  int shift, const uint32_t *__restrict__ digit_ofs /* [256] pass histogram */,
                  unsigned long long *status /* [n_tiles][256] */, uint32_t *tile_counter) {
-	__shared__ uint64_t s_keys[SO_TILE];
+	__shared__ K s_keys[SO_TILE];
 	__shared__ uint32_t s_vals[SO_TILE];
 	__shared__ uint32_t wh[SO_WARPS][SO_RADIX];
 	__shared__ uint32_t lbase[SO_RADIX];
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(SO_THREADS)
 
 	// warp-striped arrangement: warp w owns tile positions [w*32*ITEMS, (w+1)*32*ITEMS); item k of
 	// lane l sits at w*32*ITEMS + k*32 + l, so memory order == (k, lane) order inside a warp
-	uint64_t key[SO_ITEMS];
+	K key[SO_ITEMS];
 	uint32_t val[SO_ITEMS];
 	uint32_t rank[SO_ITEMS];
 	const int wbase = w * 32 * SO_ITEMS;
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(SO_THREADS)
 	for (int k = 0; k < SO_ITEMS; ++k) {
 		const int pos = wbase + k * 32 + lane;
 		const bool ok = pos < tile_cnt;
-		key[k] = ok ? keys_in[tile_base + pos] : ~0ull;
+		key[k] = ok ? keys_in[tile_base + pos] : (K)~(K)0;
 		val[k] = ok ? vals_in[tile_base + pos] : 0u;
 	}
 	// ---- early counts: warp-private digit histograms, so that the tile's counts can be published
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(SO_THREADS)
 	for (int k = 0; k < SO_ITEMS; ++k) {
 		const int i = k * SO_THREADS + threadIdx.x;
 		if (i < tile_cnt) {
-			const uint64_t kk = s_keys[i];
+			const K kk = s_keys[i];
 			const uint32_t d = (uint32_t)((kk >> shift) & 0xff);
 			const long long g = gofs[d] + i;
 			keys_out[g] = kk;
@@ -225,12 +227,13 @@ __global__ void __launch_bounds__(SO_THREADS)
 
 // Sorts n pairs by the low `key_bits` bits of the key (stable).  keys[0]/vals[0] hold the input;
 // the two buffers ping-pong; returns the index (0/1) of the buffer that holds the result.
-int radix_sort_pairs(prt_b200 *c, DevBuf &scratch, uint64_t *const keys[2], uint32_t *const vals[2],
-                     uint64_t n, int key_bits, cudaStream_t s, int *result_index) {
+template <class K>
+static int radix_sort_pairs_t(prt_b200 *c, DevBuf &scratch, K *const keys[2], uint32_t *const vals[2],
+                              uint64_t n, int key_bits, cudaStream_t s, int *result_index) {
 	*result_index = 0;
 	if (n <= 1 || key_bits <= 0)
 		return PRT_OK;
-	const int passes = std::min(SO_MAX_PASSES, (key_bits + 7) / 8);
+	const int passes = std::min<int>(sizeof(K), (key_bits + 7) / 8);
 	const uint64_t n_tiles = (n + SO_TILE - 1) / SO_TILE;
 	const size_t hist_b = (size_t)SO_MAX_PASSES * SO_RADIX * 4, ctr_b = 64;
 	const size_t status_b = (size_t)passes * n_tiles * SO_RADIX * 8;
@@ -242,11 +245,11 @@ int radix_sort_pairs(prt_b200 *c, DevBuf &scratch, uint64_t *const keys[2], uint
 	PRT_CUDA(c, cudaMemsetAsync(base, 0, hist_b + ctr_b + status_b, s));
 	const int hgrid = (int)std::min<uint64_t>((n + SO_THREADS * 8 - 1) / (SO_THREADS * 8),
 	                                          (uint64_t)c->sm_count * 8);
-	k_sweep_hist<<<hgrid, SO_THREADS, 0, s>>>(keys[0], n, passes, ghist);
+	k_sweep_hist<K><<<hgrid, SO_THREADS, 0, s>>>(keys[0], n, passes, ghist);
 	c->launches += 1;
 	int cur = 0;
 	for (int p = 0; p < passes; ++p) {
-		k_sweep_pass<<<(unsigned)n_tiles, SO_THREADS, 0, s>>>(
+		k_sweep_pass<K><<<(unsigned)n_tiles, SO_THREADS, 0, s>>>(
 		    keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, 8 * p, ghist + p * SO_RADIX,
 		    status + (size_t)p * n_tiles * SO_RADIX, ctr + p);
 		c->launches += 1;
@@ -255,6 +258,16 @@ int radix_sort_pairs(prt_b200 *c, DevBuf &scratch, uint64_t *const keys[2], uint
 	PRT_CUDA(c, cudaGetLastError());
 	*result_index = cur;
 	return PRT_OK;
+}
+
+int radix_sort_pairs(prt_b200 *c, DevBuf &scratch, uint64_t *const keys[2], uint32_t *const vals[2],
+                     uint64_t n, int key_bits, cudaStream_t s, int *result_index) {
+	return radix_sort_pairs_t<uint64_t>(c, scratch, keys, vals, n, key_bits, s, result_index);
+}
+// 32-bit keys (the ray reordering: <= 32 key bits): a pass moves 8 + 8 bytes per pair instead of 12 + 12
+int radix_sort_pairs32(prt_b200 *c, DevBuf &scratch, uint32_t *const keys[2], uint32_t *const vals[2],
+                       uint64_t n, int key_bits, cudaStream_t s, int *result_index) {
+	return radix_sort_pairs_t<uint32_t>(c, scratch, keys, vals, n, key_bits, s, result_index);
 }
 
 } // namespace prt

@@ -65,7 +65,7 @@ __device__ __forceinline__ uint32_t ray_key(const float *__restrict__ r, float3 
 // probe's fixed 4 + 4 key only decides WHETHER to sort).
 __global__ void __launch_bounds__(256)
     k_ray_keys(const float *__restrict__ rays, uint64_t n, float3 lo, float3 inv_ext, int ob, int db,
-               uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+               uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) {
 		const float *r = rays + i * 6;
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256)
 		const uint32_t ux = (uint32_t)fminf(fmaxf((dx * inv * 0.5f + 0.5f) * nd, 0.f), nd - 1.f);
 		const uint32_t uy = (uint32_t)fminf(fmaxf((dy * inv * 0.5f + 0.5f) * nd, 0.f), nd - 1.f);
 		const uint32_t uz = (uint32_t)fminf(fmaxf((dz * inv * 0.5f + 0.5f) * nd, 0.f), nd - 1.f);
-		keys[i] = (morton3(qx, qy, qz) << (3 * db)) | morton3(ux, uy, uz);
+		keys[i] = (uint32_t)((morton3(qx, qy, qz) << (3 * db)) | morton3(ux, uy, uz)); // 3 (ob + db) <= 32 bits
 		vals[i] = (uint32_t)i;
 	}
 }
@@ -277,7 +277,7 @@ int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, c
 	if (c->sort_rays && !d_counts && n >= SORT_MIN_RAYS && n < (1ull << 32) && c->n_tris > 1) {
 		auto &rs = c->rs[out.slot];
 		for (int k = 0; k < 2; ++k) {
-			PRT_CUDA(c, rs.keys[k].reserve(n * 8));
+			PRT_CUDA(c, rs.keys[k].reserve(n * 4));
 			PRT_CUDA(c, rs.vals[k].reserve(n * 4));
 		}
 		float3 lo, ie;
@@ -301,13 +301,13 @@ int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, c
 		}
 		if (do_sort) {
 			k_ray_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
-			    d_rays6, n, lo, ie, c->ray_key_ob, c->ray_key_db, rs.keys[0].as<uint64_t>(),
+			    d_rays6, n, lo, ie, c->ray_key_ob, c->ray_key_db, rs.keys[0].as<uint32_t>(),
 			    rs.vals[0].as<uint32_t>());
 			c->launches += 1;
-			uint64_t *const kk[2] = {rs.keys[0].as<uint64_t>(), rs.keys[1].as<uint64_t>()};
+			uint32_t *const kk[2] = {rs.keys[0].as<uint32_t>(), rs.keys[1].as<uint32_t>()};
 			uint32_t *const vv[2] = {rs.vals[0].as<uint32_t>(), rs.vals[1].as<uint32_t>()};
 			int cur = 0;
-			if (int rc = radix_sort_pairs(c, rs.scratch, kk, vv, n, 3 * (c->ray_key_ob + c->ray_key_db), s, &cur))
+			if (int rc = radix_sort_pairs32(c, rs.scratch, kk, vv, n, 3 * (c->ray_key_ob + c->ray_key_db), s, &cur))
 				return rc;
 			P.perm = vv[cur];
 			c->sorted_batches++;
@@ -331,8 +331,10 @@ int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, c
 	                                (c->wide_mode == 2 && (d_counts ? c->last_wide : P.perm != nullptr)));
 	if (!d_counts)
 		c->last_wide = wide;
-	if (wide)
+	if (wide) {
 		c->wide_batches++;
+		P.refill = c->refill_wide;
+	}
 	// nodes pushed on the stack are prefetched into L2 when the tree cannot live there
 	const uint64_t tree_bytes = c->n_nodes * 64 + c->n_tris * 64;
 	P.prefetch = c->prefetch == 1 || (c->prefetch == 2 && c->l2_bytes && tree_bytes > c->l2_bytes);
