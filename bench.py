@@ -356,6 +356,24 @@ def cxx_plugin_leg(w, rays, steps):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def embree_status():
+    """The reference's Embree CPU backend is the second oracle `north_star` names.  Embree 4 is an
+    external binary dependency of the reference (README.md:71-76, CMakeLists.txt:103-115) that this
+    image does not carry; tests/dropin/Makefile wires the backend into the acceptance program
+    whenever <embree4/rtcore.h> is found, and this line says which of the two happened."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "acceptance")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/acceptance not built"}
+    try:
+        out = subprocess.run([exe, "--list"], capture_output=True, text=True, timeout=120).stdout
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)}
+    if "Embree CPU backend: compiled in" in out:
+        return {"available": True, "note": "compared by oracle/_ref/acceptance (results.csv)"}
+    return {"unavailable": "Embree 4 not installed when oracle/_ref/acceptance was built "
+                           "(USE_EMBREE_CPU wiring: tests/dropin/Makefile)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -937,6 +955,7 @@ def main():
         "build_mtris_s": build["mtris_s"], "build": build,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline, "parity": parity_rep, "cpu_baseline": cpu_line,
+        "cpu_baseline_embree": embree_status() if world == 1 else None,
         "replicas": replicas, "watertight": watertight, "dynamic_without_reuse": dynamic_plain,
         "exotic_rays": int(backend.exotic_rays), "sorted_batches": int(backend.sorted_batches),
         "wall_s_timed_region": wall, "device": backend.device_name(),

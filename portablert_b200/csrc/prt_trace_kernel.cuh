@@ -70,7 +70,8 @@ struct TraceParams {
 	int coop_after;
 };
 
-constexpr int COOP_PARK = 16; // words of a parked ray state
+constexpr int COOP_PARK = 16;      // words of a parked ray state
+constexpr int COOP_STRAGGLERS = 4; // a warp with at most this many busy lanes hands them over
 
 // Per-thread stack: SMEM_STACK entries in shared memory, the rest in global memory.
 // PF (the wide-node kernels, i.e. scenes that do not fit L2): nodes are prefetched into L2 as they
@@ -399,6 +400,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PRT_MIN_BLOCKS) k_trace(const T
 	bool has_ray = false;
 	bool exhausted = false; // warp-uniform: the global counter ran past the last ray
 	int tail_iters = 0;     // warp-uniform: iterations since then
+	bool handover = false;  // warp-uniform: the stragglers of this warp go to k_coop
 	s.cur = PRT_DONE;
 
 	for (;;) {
@@ -481,34 +483,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, PRT_MIN_BLOCKS) k_trace(const T
 			const int busy = __popc(leafm | nodem);
 			if (busy == 0 || (!exhausted && busy < P.refill))
 				break; // (lanes parked at a triangle stay parked across the refill)
-			// still busy long after the end of the batch: hand the unfinished rays over to k_coop
-			if (COOP && exhausted && P.coop_after > 0 && ++tail_iters > P.coop_after) {
-				if (leaf || (has_ray && at_node(s.cur))) {
-					const uint32_t at = atomicAdd(P.coop, 1u);
-					if (at < P.coop_cap && (uint32_t)stack.sp <= P.coop_depth) {
-						uint32_t *p = P.coop + 4 + (size_t)at * P.coop_rec;
-						__stcg(p + 0, (uint32_t)ray);
-						__stcg(p + 1, (uint32_t)(ray >> 32));
-#pragma unroll
-						for (int a = 0; a < 3; ++a) {
-							__stcg(p + 2 + a, f2u(r.o[a]));
-							__stcg(p + 5 + a, f2u(r.d[a]));
-						}
-						__stcg(p + 8, f2u(s.t_best));
-						__stcg(p + 9, f2u(s.u_best));
-						__stcg(p + 10, f2u(s.v_best));
-						__stcg(p + 11, s.prim_best);
-						__stcg(p + 12, (uint32_t)s.cur);
-						__stcg(p + 13, (uint32_t)stack.sp);
-						uint2 *st = reinterpret_cast<uint2 *>(p + COOP_PARK);
-						for (int k = 0; k < stack.sp; ++k)
-							__stcg(st + k, stack.peek(k));
-						has_ray = false; // (its record is written by k_coop)
-						s.cur = PRT_DONE;
-					} // else: the list is full -- this lane keeps tracing here
-				}
-				tail_iters = 0; // lanes that could not be handed over try again later
-				continue;
+			// stragglers long after the end of the batch are handed over to k_coop (below)
+			if (COOP && exhausted && ++tail_iters > P.coop_after &&
+			    (busy <= COOP_STRAGGLERS || tail_iters > 8 * P.coop_after)) {
+				handover = P.coop_after > 0;
+				if (handover)
+					break;
 			}
 			// (once the batch is exhausted nobody waits: what is left is the tail of the kernel,
 			// bound by the latency of its longest rays)
@@ -516,6 +496,36 @@ __global__ void __launch_bounds__(TRACE_THREADS, PRT_MIN_BLOCKS) k_trace(const T
 				if (leaf)
 					trav_leaf_step<ANYHIT, WANT_UV, TRACK_PRIM, COUNT, FAST, WT>(
 					    s, stack, P.tris, r, opts, &wr, my_idir, idir_stride);
+			}
+		}
+		// Hand the rays this warp is still tracing -- state and pending stack, one record each -- over
+		// to k_coop, which finishes every one of them with a whole warp (see k_coop above).
+		if (COOP && handover) {
+			handover = false;
+			tail_iters = 0; // lanes that cannot be handed over (list full) keep tracing and try again
+			if (has_ray && s.cur != PRT_DONE) {
+				const uint32_t at = atomicAdd(P.coop, 1u);
+				if (at < P.coop_cap && (uint32_t)stack.sp <= P.coop_depth) {
+					uint32_t *p = P.coop + 4 + (size_t)at * P.coop_rec;
+					__stcg(p + 0, (uint32_t)ray);
+					__stcg(p + 1, (uint32_t)(ray >> 32));
+#pragma unroll
+					for (int a = 0; a < 3; ++a) {
+						__stcg(p + 2 + a, f2u(r.o[a]));
+						__stcg(p + 5 + a, f2u(r.d[a]));
+					}
+					__stcg(p + 8, f2u(s.t_best));
+					__stcg(p + 9, f2u(s.u_best));
+					__stcg(p + 10, f2u(s.v_best));
+					__stcg(p + 11, s.prim_best);
+					__stcg(p + 12, (uint32_t)s.cur);
+					__stcg(p + 13, (uint32_t)stack.sp);
+					uint2 *st = reinterpret_cast<uint2 *>(p + COOP_PARK);
+					for (int k = 0; k < stack.sp; ++k)
+						__stcg(st + k, stack.peek(k));
+					has_ray = false; // (its record is written by k_coop)
+					s.cur = PRT_DONE;
+				}
 			}
 		}
 	}

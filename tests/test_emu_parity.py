@@ -446,3 +446,46 @@ def test_fuzz_random_scenes_default_and_watertight(seed, oracle, emu):
     got = emu.trace(allrays, watertight=True)
     for k in ("valid", "t", "pid", "u", "v"):
         assert np.array_equal(got[k], want[k], equal_nan=True), (seed, k)
+
+
+def test_pruning_on_slivers_and_grazing_rays(emu, oracle):
+    """Pruning drops a subtree when its box entry distance exceeds t_best + slack; that is exact in
+    real arithmetic, and the slack has to cover the rounding of Moeller-Trumbore's t against the
+    slab test.  Ill-conditioned candidates -- needle and sliver triangles (tiny determinant), rays
+    grazing a triangle's plane or running along its edges -- are where a computed t could leave the
+    triangle's own box interval.  Pruned == exhaustive == the oracle on such inputs."""
+    g = np.random.default_rng(77)
+    n = 3000
+    a = g.uniform(-1, 1, (n, 3)).astype(np.float32)
+    along = g.normal(size=(n, 3)).astype(np.float32)
+    along /= np.linalg.norm(along, axis=1, keepdims=True)
+    side = g.normal(size=(n, 3)).astype(np.float32)
+    length = (10.0 ** g.uniform(-2, 0.5, (n, 1))).astype(np.float32)
+    width = (10.0 ** g.uniform(-7, -3, (n, 1))).astype(np.float32)        # aspect ratios 1e3 .. 1e7
+    b = a + along * length
+    c = a + along * length * g.uniform(0.2, 0.8, (n, 1)).astype(np.float32) + side * width
+    tris = np.concatenate([a, b, c], 1).astype(np.float32)
+    # rays: (1) through a point of a sliver, nearly inside its plane; (2) along its long edge,
+    # offset by ulps; (3) random
+    k = g.integers(0, n, 6000)
+    p = (a[k] + (b[k] - a[k]) * g.uniform(0.1, 0.9, (6000, 1)).astype(np.float32)).astype(np.float32)
+    nrm = np.cross(b[k] - a[k], c[k] - a[k])
+    nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-30)
+    graze = (along[k] + nrm * (10.0 ** g.uniform(-6, -1, (6000, 1)))).astype(np.float32)
+    o = (p - graze * g.uniform(0.5, 3.0, (6000, 1)).astype(np.float32)).astype(np.float32)
+    rays1 = np.concatenate([o, graze], 1)
+    o2 = (a[k] - along[k] * 0.5 + side[k] * (10.0 ** g.uniform(-8, -5, (6000, 1)))).astype(np.float32)
+    rays2 = np.concatenate([o2, along[k]], 1).astype(np.float32)
+    rays = np.concatenate([rays1, rays2, scenes.incoherent_rays(4000, [-2] * 3, [2] * 3, 9)]).astype(np.float32)
+    oracle.build(tris)
+    ref = oracle.trace(rays)
+    emu.build(tris, 16)
+    full = emu.trace(rays, prune=0)
+    pruned = emu.trace(rays, prune=1)
+    assert ref["valid"].sum() > 500
+    parity.assert_parity(parity.compare(ref, full, tris, rays, oracle))
+    diff = [f for f in ("t", "u", "v", "pid", "valid") if not np.array_equal(full[f], pruned[f], equal_nan=True)]
+    assert not diff, diff
+    emu.treelet(2)
+    pruned_opt = emu.trace(rays, prune=1)
+    assert all(np.array_equal(full[f], pruned_opt[f], equal_nan=True) for f in ("t", "pid", "valid"))
