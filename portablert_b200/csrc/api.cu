@@ -209,7 +209,7 @@ static int create_one(prt_b200 **out, int device) {
 	if (const char *e = std::getenv("PRT_B200_PIPE_TRACE"))
 		c->pipe_trace = std::atoi(e) != 0;
 	if (const char *e = std::getenv("PRT_B200_CHUNK_LOG2"))
-		c->chunk_log2 = std::max(10, std::min(19, std::atoi(e)));
+		c->chunk_log2 = std::max(10, std::min(24, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_REFILL"))
 		c->refill = c->refill_wide = std::max(0, std::min(32, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_REFILL_WIDE"))
@@ -827,7 +827,7 @@ static int nearest_hits_device(prt_b200 *c, const float *rays6, uint64_t n, uint
 		CH = std::max<uint64_t>(CH, 1ull << 19); // bound by the host-side staging copies: few large ones
 	if (c->chunk_log2 > 0)
 		CH = 1ull << c->chunk_log2;
-	CH = std::min<uint64_t>(std::min<uint64_t>(CH, CH_MAX), n);
+	CH = std::min<uint64_t>(std::min<uint64_t>(CH, c->chunk_log2 > 0 ? (1ull << 24) : CH_MAX), n);
 	std::vector<uint64_t> start; // chunk k = rays [start[k], start[k+1])
 	for (uint64_t at = 0; at < n; at += CH)
 		start.push_back(at);

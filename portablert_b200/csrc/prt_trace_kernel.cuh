@@ -70,8 +70,7 @@ struct TraceParams {
 	int coop_after;
 };
 
-constexpr int COOP_PARK = 16;      // words of a parked ray state
-constexpr int COOP_STRAGGLERS = 4; // a warp with at most this many busy lanes hands them over
+constexpr int COOP_PARK = 16; // words of a parked ray state
 
 // Per-thread stack: SMEM_STACK entries in shared memory, the rest in global memory.
 // PF (the wide-node kernels, i.e. scenes that do not fit L2): nodes are prefetched into L2 as they
@@ -483,9 +482,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, PRT_MIN_BLOCKS) k_trace(const T
 			const int busy = __popc(leafm | nodem);
 			if (busy == 0 || (!exhausted && busy < P.refill))
 				break; // (lanes parked at a triangle stay parked across the refill)
-			// stragglers long after the end of the batch are handed over to k_coop (below)
-			if (COOP && exhausted && ++tail_iters > P.coop_after &&
-			    (busy <= COOP_STRAGGLERS || tail_iters > 8 * P.coop_after)) {
+			// rays still being traced long after the end of the batch are handed over to k_coop (below)
+			if (COOP && exhausted && ++tail_iters > P.coop_after) {
 				handover = P.coop_after > 0;
 				if (handover)
 					break;
