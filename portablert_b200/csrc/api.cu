@@ -218,6 +218,8 @@ static int create_one(prt_b200 **out, int device) {
 		c->leaf_votes = std::max(1, std::min(32, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_COOP"))
 		c->coop_after = std::max(0, std::min(1 << 20, std::atoi(e)));
+	if (const char *e = std::getenv("PRT_B200_COOP_SP"))
+		c->coop_min_sp = std::max(0, std::min(64, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_COOP_BLOCKS"))
 		c->coop_blocks = std::max(1, std::min(8, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_PREFETCH"))
@@ -248,6 +250,33 @@ static std::vector<int> cc10_devices() {
 			v.push_back(d);
 	}
 	return v;
+}
+
+// Single-process NCCL communicators over the context's devices (ncclCommInitAll), created when
+// the context is: that takes about a second for 8 GPUs and must not land in the first set_tris.
+// Where libnccl cannot be loaded or initialised the broadcast uses peer copies.
+static void init_nccl(prt_b200 *c) {
+	const auto devs = all_devices(c);
+	if (c->bcast_mode != 0 || c->nccl || devs.size() < 2)
+		return;
+	auto *api = new prt::NcclApi();
+	bool ok = api->load();
+	if (ok) {
+		std::vector<int> ids;
+		for (auto *d : devs)
+			ids.push_back(d->device);
+		c->nccl_comms.assign(devs.size(), nullptr);
+		ok = api->CommInitAll(c->nccl_comms.data(), (int)devs.size(), ids.data()) == 0;
+		if (!ok)
+			c->nccl_comms.clear();
+		cudaSetDevice(c->device);
+	}
+	if (ok)
+		c->nccl = api;
+	else {
+		delete api;
+		c->bcast_mode = 1;
+	}
 }
 
 int prt_b200_create_multi(prt_b200 **out, int n_gpus) {
@@ -306,6 +335,7 @@ int prt_b200_create_multi(prt_b200 **out, int n_gpus) {
 				}
 		}
 		c->name += " x" + std::to_string(n_gpus);
+		init_nccl(c);
 	}
 	cudaSetDevice(c->device);
 	*out = c;
@@ -514,26 +544,6 @@ static int broadcast_tris(prt_b200 *c, const float *src, uint64_t n) {
 	PRT_CUDA(c, cudaSetDevice(c->device));
 	if (bytes == 0)
 		return PRT_OK;
-	if (c->bcast_mode == 0 && !c->nccl) {
-		auto *api = new prt::NcclApi();
-		bool ok = api->load();
-		if (ok) {
-			std::vector<int> ids;
-			for (auto *d : devs)
-				ids.push_back(d->device);
-			c->nccl_comms.assign(devs.size(), nullptr);
-			ok = api->CommInitAll(c->nccl_comms.data(), (int)devs.size(), ids.data()) == 0;
-			if (!ok)
-				c->nccl_comms.clear();
-			cudaSetDevice(c->device);
-		}
-		if (ok)
-			c->nccl = api;
-		else {
-			delete api;
-			c->bcast_mode = 1;
-		}
-	}
 	if (c->nccl) {
 		int rc = c->nccl->GroupStart();
 		for (size_t i = 0; i < devs.size() && rc == 0; ++i)

@@ -20,7 +20,7 @@ constexpr int SMEM_STACK = PRT_SMEM_STACK;
 #endif
 // node steps between two votes of the warp (leaf phase? enough lanes busy?)
 #ifndef PRT_NODE_BURST
-#define PRT_NODE_BURST 2
+#define PRT_NODE_BURST 4
 #endif
 
 struct TraceParams {
@@ -68,6 +68,7 @@ struct TraceParams {
 	uint2 *coop_lifo;        // k_coop: LIFO area, coop_lifo_cap entries per warp of its grid
 	uint32_t coop_lifo_cap;
 	int coop_after;
+	int coop_min_sp; // hand over only rays with at least this many stacked subtrees
 };
 
 constexpr int COOP_PARK = 16; // words of a parked ray state
@@ -501,9 +502,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, PRT_MIN_BLOCKS) k_trace(const T
 		if (COOP && handover) {
 			handover = false;
 			tail_iters = 0; // lanes that cannot be handed over (list full) keep tracing and try again
-			if (has_ray && s.cur != PRT_DONE) {
+			// (only rays with several pending subtrees: a ray walking down a single path offers the 32
+			// lanes nothing to share and finishes sooner where it is)
+			if (has_ray && s.cur != PRT_DONE && stack.sp >= P.coop_min_sp && (uint32_t)stack.sp <= P.coop_depth) {
 				const uint32_t at = atomicAdd(P.coop, 1u);
-				if (at < P.coop_cap && (uint32_t)stack.sp <= P.coop_depth) {
+				if (at < P.coop_cap) {
 					uint32_t *p = P.coop + 4 + (size_t)at * P.coop_rec;
 					__stcg(p + 0, (uint32_t)ray);
 					__stcg(p + 1, (uint32_t)(ray >> 32));

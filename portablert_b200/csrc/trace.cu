@@ -217,6 +217,7 @@ static int launch_kernel(prt_b200 *c, KernelFn fn, int cache_slot, uint32_t mask
 		P.coop_lifo = c->coop_lifo[slot].as<uint2>();
 		P.coop_lifo_cap = lifo_cap;
 		P.coop_after = c->coop_after;
+		P.coop_min_sp = c->coop_min_sp;
 	}
 	if (timed)
 		PRT_CUDA(c, cudaEventRecord(c->ev_k0, s));

@@ -1,12 +1,16 @@
 #!/usr/bin/env python
-"""Turn the bench JSON lines under gpurun_out/ into profiles/r01_results.md (numbers measured on
-the GPU box without a profiler attached)."""
+"""Turn the bench JSON lines under gpurun_out/r2/ into profiles/r02_results.md (numbers measured on
+the GPU box without a profiler attached).
+
+    python tools/summarise_results.py            # reads gpurun_out/r2/final_<cfg>.json, final_c4_n<N>.json
+"""
 import json
 import os
-import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-G = os.path.join(ROOT, "gpurun_out")
+G = os.path.join(ROOT, "gpurun_out", "r2")
+R1 = {"c2": 6782, "c3": 11263, "c3b": 5381, "c5": 5834, "c4": 2459}  # profiles/r01_results.md
+R1_E2E = {"c2": 1264, "c3": 1433, "c3b": 1866, "c5": 1751, "c4": 1080}
 
 
 def load(name):
@@ -18,50 +22,62 @@ def load(name):
 
 
 def main():
-    out = ["# Round 1 -- measured results (one B200 unless stated; no profiler attached)\n",
-           "Device-timed: rays resident in HBM, SoA outputs, CUDA events taken by the library on the "
-           "stream the kernels run on, L2 flushed (256 MiB memset) between timed steps, mean of the "
-           "timed steps.  e2e: host buffers in, host `HitReg` records out through "
-           "`prt_b200_nearest_hits` (pinned host memory, H2D + kernels + D2H inside the timed region).\n",
-           "Static scenes (C2, C3, C3B, C4) are traced on the tree the default lazy mode leaves after "
-           "max(32 rays per triangle, 8 Mi rays): the LBVH optimised by 2 treelet passes; C5 calls "
-           "set_tris before every step (dynamic scene, see below).  `build ms` = set_tris as called "
-           "(plain LBVH); `build+opt ms` = the same with the optimisation inside set_tris.\n",
-           "| config | tris | rays | tags | trace ms | Mrays/s | nodes/ray | tris/ray | B/ray | "
-           "fetched GB/s | of L2 read peak | build ms | Mtris/s | build+opt ms | Mtris/s | tree height | e2e Mrays/s |",
-           "|---|---:|---:|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|"]
+    out = ["# Round 2 -- measured results (one B200 unless stated; no profiler attached)\n",
+           "`python bench.py --config <cfg> --steps 20 --warmup 5`.  Device-timed: rays resident in HBM, "
+           "SoA outputs, CUDA events taken by the library on the stream the kernels run on (ray "
+           "reordering included), L2 flushed (256 MiB memset) between timed steps.  e2e: host buffers in, "
+           "host `HitReg` records out through `prt_b200_nearest_hits` (pinned host memory, H2D + kernels "
+           "+ D2H inside the timed region); `C++` = the reference's real signature (std::vector in, fresh "
+           "std::vector out) timed by `oracle/_ref/bench_cxx`.  `parity` = section-8c comparator against "
+           "the unmodified reference CPU backend at FULL size, inside the bench run (rays checked / "
+           "valid mismatches / primitive-id mismatches / exact ties / t bit-exact).\n",
+           "| config | tris | rays | tags | step ms | Mrays/s | round 1 | kernel ms | nodes/ray | tris/ray | B/ray | "
+           "roof | frac | DRAM frac | build ms | Mtris/s | e2e Mrays/s | round 1 | pageable | C++ | parity |",
+           "|---|---:|---:|---|---:|---:|---:|---:|---:|---:|---:|---|---:|---:|---:|---:|---:|---:|---:|---:|---|"]
     for cfg in ("c2", "c3", "c3b", "c5", "c4"):
-        d = load(f"bench_{cfg}.json")
+        d = load(f"final_{cfg}.json")
         if not d:
             continue
-        r = d["roofline"]
-        out.append(f"| {cfg.upper()} | {d['config']['tris']:,} | {d['config']['rays_per_gpu']:,} | "
-                   f"mask {d['config']['tag_mask']} | {d['ms_per_step']:.3f} | {d['value']:.0f} | "
-                   f"{r['nodes_per_ray']:.1f} | {r['tris_per_ray']:.2f} | {r['bytes_per_ray']:.0f} | "
-                   f"{r['achieved']:.0f} | {r['frac_of_l2']:.2f} | {d['build']['ms']:.3f} | "
-                   f"{d['build']['mtris_s']:.0f} | {d['build']['ms_with_optimisation']:.3f} | "
-                   f"{d['build']['mtris_s_with_optimisation']:.0f} | {d['build']['tree_height'] or '-'} | "
-                   f"{d['e2e']['value']:.0f} |")
-    d = load("bench_c2.json")
+        r, e, p = d["roofline"], d["e2e"], d.get("parity") or {}
+        cx = (e.get("cxx_plugin") or {}).get("value")
+        par = (f"{p.get('checked_rays', 0):,} / {p.get('valid_mismatch')} / {p.get('pid_mismatch')} / "
+               f"{p.get('pid_ties')} / {p.get('t_bitexact')}") if p else "-"
+        dram = r.get("dram_frac_of_hbm")
+        out.append(f"| {cfg.upper()} | {d['config']['tris']:,} | {d['config']['rays']:,} | "
+                   f"mask {d['config']['tag_mask']} | {d['ms_per_step']:.3f} | **{d['value']:.0f}** | {R1[cfg]} | "
+                   f"{r['kernel_ms']:.3f} | {r['nodes_per_ray']:.1f} | {r['tris_per_ray']:.2f} | "
+                   f"{r['bytes_per_ray']:.0f} | {r['bound']} | {r['frac']:.2f} | "
+                   f"{('%.2f' % dram) if dram else '-'} | {d['build']['ms']:.3f} | {d['build']['mtris_s']:.0f} | "
+                   f"{e['value']:.0f} | {R1_E2E[cfg]} | {e.get('pageable_value', 0):.0f} | "
+                   f"{('%.0f' % cx) if cx else '-'} | {par} |")
+    d = load("final_c4.json")
     if d:
-        r = d["roofline"]
-        out.append(f"\nMeasured on the box in the same run: L2 read bandwidth {r['l2_read_gbs_measured']:.0f} GB/s "
-                   f"(32 MiB re-read), HBM read bandwidth {r['hbm_read_gbs_measured']:.0f} GB/s (2 GiB re-read); "
-                   f"roofline peak used for `roofline.frac`: {r['peak']} GB/s, {r['peak_source']}.  "
-                   f"Clocks during the timed region: {d['clocks']}.\n")
-        c = d.get("cpu_baseline") or {}
-        if c and "value" in c:
+        r, c, e = d["roofline"], d.get("cpu_baseline") or {}, d["e2e"]
+        out.append(f"\nC4 is the headline (`bench.py` default).  Roofline denominators: HBM "
+                   f"{r['peak'] if r['bound'] == 'hbm' else '-'} GB/s ({r['peak_source']}); measured on the box in "
+                   f"the same run: L2 read {r['l2_read_gbs_measured']:.0f} GB/s, HBM read "
+                   f"{r['hbm_read_gbs_measured']:.0f} GB/s.  ncu (profiles/r02_trace_c4_full.md): "
+                   f"{(r.get('traffic') or 0) / 1e9:.1f} GB of DRAM traffic per launch.  Clocks during the timed "
+                   f"region: {d['clocks']}.\n")
+        if "value" in c:
             out.append(f"CPU reference beside it (unmodified reference CPU backend, oracle/_ref): "
-                       f"{c['value']:.1f} Mrays/s on {c['cores']} threads ({c['cpu']}), {c['sample']}; "
-                       f"`set_tris` {c['build_mtris_s']:.3f} Mtris/s (1 thread).  C2 ratios: device-timed "
-                       f"{d['value'] / c['value']:.0f}x, e2e (pinned) {d['e2e']['value'] / c['value']:.0f}x, "
-                       f"e2e (pageable) {d['e2e'].get('pageable_value', 0) / c['value']:.0f}x, build "
-                       f"{d['build']['mtris_s'] / c['build_mtris_s']:.0f}x.\n")
-        pm = d.get("per_mask_mrays_s")
-        if pm:
-            out.append("C2, all 31 tag combinations (device-timed Mrays/s): " +
-                       ", ".join(f"{k} {v:.0f}" for k, v in pm.items()) + "\n")
-    d5 = load("bench_c5.json")
+                       f"{c['value']:.2f} Mrays/s on {c['cores']} threads ({c['cpu']}), {c['sample']}; "
+                       f"`set_tris` {c['build_mtris_s']:.3f} Mtris/s ({c['build_s']:.0f} s, 1 thread).  C4 ratios: "
+                       f"device-timed {d['value'] / c['value']:.0f}x, e2e (pinned) {e['value'] / c['value']:.0f}x, "
+                       f"e2e (C++ signature) {((e.get('cxx_plugin') or {}).get('value') or 0) / c['value']:.0f}x, "
+                       f"build {d['build']['mtris_s'] / c['build_mtris_s']:.0f}x.\n")
+        pc = e.get("pcie") or {}
+        out.append(f"C4 e2e: {e['ms_per_step']:.1f} ms per 10^8 rays with pinned buffers ({e['h2d_bytes_per_step'] / 1e9:.1f} GB "
+                   f"in, {e['d2h_bytes_per_step'] / 1e9:.1f} GB out; the bare copies take {pc.get('floor_ms', 0):.1f} ms: "
+                   f"{e.get('frac_of_pcie_floor', 0):.2f} of the PCIe floor); pageable numpy "
+                   f"{e.get('pageable_ms_per_step', 0):.0f} ms ({e.get('pageable_d2h_bytes', 0) / 1e9:.1f} GB out: packed); "
+                   f"C++ signature {(e.get('cxx_plugin') or {}).get('ms_mean', 0):.0f} ms, digest equal to the device "
+                   f"result: {(e.get('cxx_plugin') or {}).get('digest_equals_device_result')}.\n")
+        w = d.get("watertight")
+        if w:
+            out.append(f"Opt-in watertight test on C4: {w['value']:.0f} Mrays/s, `valid` differs on "
+                       f"{w['valid_differs']} rays, t differs by > 1e-5 relative on {w['t_rel_gt_1e-5']}.\n")
+    d5 = load("final_c5.json")
     if d5 and d5.get("dynamic_without_reuse"):
         r, b = d5["dynamic_without_reuse"], d5["build"]
         out.append(f"C5 is the dynamic scene: every step calls set_tris with the next of 4 distinct frames of the "
@@ -71,44 +87,30 @@ def main():
                    f"{d5['ms_per_step']:.3f} ms = frame {b['set_tris_ms_steady'] + d5['ms_per_step']:.3f} ms.  Without "
                    f"reuse (mode 2, plain LBVH rebuilt every frame): set_tris {r['set_tris_ms']:.3f} ms + traversal "
                    f"{r['trace_ms']:.3f} ms ({r['value']:.0f} Mrays/s) = frame {r['frame_ms']:.3f} ms.\n")
-    out.append("Opt-in watertight triangle test beside the default (same rays, same tree state): "
-               "Mrays/s, rays whose `valid` differs, rays whose t differs by more than 1e-5 relative:\n")
-    out.append("| config | default Mrays/s | watertight Mrays/s | valid differs | t differs > 1e-5 rel |")
-    out.append("|---|---:|---:|---:|---:|")
-    for cfg in ("c2", "c3", "c3b", "c5", "c4"):
-        d = load(f"bench_{cfg}.json")
-        if d and d.get("watertight"):
-            w = d["watertight"]
-            out.append(f"| {cfg.upper()} | {d['value']:.0f} | {w['value']:.0f} | {w['valid_differs']} | "
-                       f"{w['t_rel_gt_1e-5']} |")
-    out.append("")
-    ref = load("bench_c2_ref.json")
-    if ref:
-        out.append(f"`bench.py --impl reference` (same box): {ref['value']:.1f} Mrays/s, "
-                   f"{ref['cpu_baseline']['cores']} threads, build {ref['build_mtris_s']:.3f} Mtris/s.\n")
     rows = []
     for n in (1, 2, 4, 8):
-        d = load("bench_c2.json") if n == 1 else load(f"bench_c2_n{n}.json")
+        d = load("final_c4.json") if n == 1 else load(f"final_c4_n{n}.json")
         if d:
             e = d["e2e"]
             floor = e.get("pcie_concurrent_floor_ms") or (e.get("pcie") or {}).get("floor_ms")
-            rows.append(f"| {n} | {d['value']:.0f} | {d['ms_per_step']:.3f} | {e['value']:.0f} | "
-                        f"{e['ms_per_step']:.2f} | {('%.2f' % floor) if floor else '-'} |")
-    prev = os.path.join(ROOT, "profiles", "r01_results_earlier.md")
-    if os.path.exists(prev):
-        out.append(open(prev).read())
+            ok = e.get("digest_equals_per_rank_device_results", e.get("digest_equals_device_result"))
+            rep = (d.get("replicas") or {}).get("digests_identical_across_gpus", "-")
+            rows.append(f"| {n} | {d['value']:.0f} | {d['ms_per_step']:.2f} | {d['rays_per_gpu']:,} | {e['value']:.0f} | "
+                        f"{e['ms_per_step']:.1f} | {('%.1f' % floor) if floor else '-'} | {ok} | {rep} |")
     if len(rows) > 1:
-        out.append("## Multi-GPU (C2, weak scaling: N frames of 2 073 600 rays, one rank per GPU, torchrun)\n")
-        out.append("| GPUs | device-timed Mrays/s (whole job) | ms/step (max over ranks) | e2e Mrays/s | e2e ms/step | bare copies, all ranks at once (ms) |")
-        out.append("|---:|---:|---:|---:|---:|---:|")
+        out.append("## Multi-GPU (C4, STRONG scaling: the same 10^8 rays over N GPUs; torchrun, one rank per GPU)\n")
+        out.append("Device-timed: rank r traces the contiguous slice [r R/N, (r+1) R/N) on its own replica of the "
+                   "BVH (triangles NCCL-broadcast from rank 0), max over ranks.  e2e: ONE process drives all N "
+                   "GPUs through the library's multi-GPU context (`prt_b200_create_multi`) on the whole pinned "
+                   "host batch; `floor` = all GPUs copying their slices both ways at once, no kernels.\n")
+        out.append("| GPUs | device-timed Mrays/s (whole job) | ms/step (max over ranks) | rays per GPU | e2e Mrays/s | "
+                   "e2e ms/step | copy floor ms | e2e digest == ranks' device results | replicas identical |")
+        out.append("|---:|---:|---:|---:|---:|---:|---:|---|---|")
         out += rows
-        out.append("\nThe device-timed metric scales with the GPUs (every rank traces its slice on its own "
-                   "identical BVH, no collective on the data path).  The e2e call is bound by the box's "
-                   "host<->device path: with all ranks copying their slices both ways at once and no "
-                   "kernel at all, the copies alone take the time in the last column (N=4: the e2e call "
-                   "runs at 98 % of it) -- these boxes are virtual machines whose GPUs share the "
-                   "PCIe/IOMMU path, about 140 GB/s in total.\n")
-    open(os.path.join(ROOT, "profiles", "r01_results.md"), "w").write("\n".join(out) + "\n")
+        out.append("\nThe device-timed metric scales with the GPUs (no collective on the data path).  The e2e "
+                   "call is bound by the box's shared host<->device path (about 130 GB/s in total on these "
+                   "virtual machines): it runs at the copy floor from N = 2 on.\n")
+    open(os.path.join(ROOT, "profiles", "r02_results.md"), "w").write("\n".join(out) + "\n")
     print("\n".join(out))
 
 
