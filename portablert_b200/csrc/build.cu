@@ -55,23 +55,79 @@ __device__ __forceinline__ void load_tri_tile(float *sm, const float *tris9, uin
 	}
 }
 
+// Streams the triangle array through shared memory tile by tile (grid-stride) and calls
+// body(tile in shared memory, first triangle, count) for each.  Full tiles -- 256 triangles =
+// 9 216 bytes, a multiple of 16 -- are fetched by the bulk-copy engine (cp.async.bulk: UBLKCP on
+// sm_100a, completion on an mbarrier), double-buffered: one thread issues the copy of the block's
+// NEXT tile before the block computes on the current one, so no thread spends instructions or
+// registers on the load and the copy overlaps the arithmetic.  A ragged last tile or a triangle
+// array that is not 16-byte aligned takes the plain loader.
+template <class F>
+__device__ __forceinline__ void for_each_tri_tile(const float *__restrict__ tris9, uint64_t n,
+                                                  float (*sm)[TT * 9], uint64_t *bar, F body) {
+	constexpr uint32_t TILE_BYTES = TT * 36;
+	const uint64_t ntiles = (n + TT - 1) / TT;
+	const bool aligned = (reinterpret_cast<uintptr_t>(tris9) & 15) == 0;
+	const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bar);
+	const uint32_t sm0 = (uint32_t)__cvta_generic_to_shared(&sm[0][0]);
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	auto bulk = [&](uint64_t tile) { return aligned && (tile + 1) * TT <= n; };
+	auto issue = [&](uint64_t tile, int buf) {
+		const uint32_t bb = bar0 + 8 * buf, dst = sm0 + TILE_BYTES * buf;
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bb), "r"(TILE_BYTES)
+		             : "memory");
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		             ::"r"(dst), "l"(tris9 + tile * (uint64_t)(TT * 9)), "r"(TILE_BYTES), "r"(bb)
+		             : "memory");
+	};
+	uint64_t tile = blockIdx.x;
+	uint32_t phase = 0; // bit b: parity the next completion of buffer b will have
+	if (threadIdx.x == 0 && tile < ntiles && bulk(tile))
+		issue(tile, 0);
+	for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+		const int buf = it & 1;
+		const uint64_t next = tile + gridDim.x;
+		// (the other buffer was released by the __syncthreads that ended the previous iteration)
+		if (threadIdx.x == 0 && next < ntiles && bulk(next))
+			issue(next, buf ^ 1);
+		const uint64_t first = tile * TT;
+		const int cnt = (int)min((uint64_t)TT, n - first);
+		if (bulk(tile)) {
+			const uint32_t bb = bar0 + 8 * buf, parity = (phase >> buf) & 1u;
+			uint32_t done = 0;
+			while (!done)
+				asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; "
+				             "selp.u32 %0, 1, 0, p; }"
+				             : "=r"(done)
+				             : "r"(bb), "r"(parity)
+				             : "memory");
+			phase ^= 1u << buf;
+		} else {
+			load_tri_tile(sm[buf], tris9, first, cnt);
+			__syncthreads();
+		}
+		body(sm[buf], first, cnt);
+		__syncthreads();
+	}
+}
+
 // ------------------------------------------------------------------------------------------------
 // 1. centroid bounds
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TT) k_bounds(const float *__restrict__ tris9, uint64_t n,
                                                uint32_t *__restrict__ bounds_ord) {
-	__shared__ __align__(16) float sm[TT * 9];
+	__shared__ __align__(128) float sm[2][TT * 9];
+	__shared__ __align__(8) uint64_t bar[2];
 	__shared__ float red[6][TT / 32];
 	float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-	const uint64_t ntiles = (n + TT - 1) / TT;
-	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-		const uint64_t first = tile * TT;
-		const int cnt = (int)min((uint64_t)TT, n - first);
-		__syncthreads();
-		load_tri_tile(sm, tris9, first, cnt);
-		__syncthreads();
+	for_each_tri_tile(tris9, n, sm, bar, [&](const float *tile, uint64_t, int cnt) {
 		if ((int)threadIdx.x < cnt) {
-			Box b = tri_box(sm + threadIdx.x * 9);
+			Box b = tri_box(tile + threadIdx.x * 9);
 #pragma unroll
 			for (int a = 0; a < 3; ++a) {
 				float c = 0.5f * b.lo[a] + 0.5f * b.hi[a];
@@ -79,7 +135,7 @@ __global__ void __launch_bounds__(TT) k_bounds(const float *__restrict__ tris9, 
 				hi[a] = fmaxf(hi[a], c);
 			}
 		}
-	}
+	});
 #pragma unroll
 	for (int a = 0; a < 3; ++a) {
 #pragma unroll
@@ -122,7 +178,8 @@ __global__ void __launch_bounds__(TT) k_morton(const float *__restrict__ tris9, 
                                                const uint32_t *__restrict__ bounds_ord, int bits,
                                                uint64_t *__restrict__ keys,
                                                uint32_t *__restrict__ vals) {
-	__shared__ __align__(16) float sm[TT * 9];
+	__shared__ __align__(128) float sm[2][TT * 9];
+	__shared__ __align__(8) uint64_t bar[2];
 	float cmin[3], scale[3];
 	const float cells = (float)(1u << bits);
 #pragma unroll
@@ -132,15 +189,9 @@ __global__ void __launch_bounds__(TT) k_morton(const float *__restrict__ tris9, 
 		scale[a] = (ext > 0.0f && ext < INFINITY) ? cells / ext : 0.0f;
 	}
 	const uint32_t qmax = (1u << bits) - 1u;
-	const uint64_t ntiles = (n + TT - 1) / TT;
-	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-		const uint64_t first = tile * TT;
-		const int cnt = (int)min((uint64_t)TT, n - first);
-		__syncthreads();
-		load_tri_tile(sm, tris9, first, cnt);
-		__syncthreads();
+	for_each_tri_tile(tris9, n, sm, bar, [&](const float *tile, uint64_t first, int cnt) {
 		if ((int)threadIdx.x < cnt) {
-			Box b = tri_box(sm + threadIdx.x * 9);
+			Box b = tri_box(tile + threadIdx.x * 9);
 			uint32_t q[3];
 #pragma unroll
 			for (int a = 0; a < 3; ++a) {
@@ -152,7 +203,7 @@ __global__ void __launch_bounds__(TT) k_morton(const float *__restrict__ tris9, 
 			keys[first + threadIdx.x] = morton3(q[0], q[1], q[2]);
 			vals[first + threadIdx.x] = (uint32_t)(first + threadIdx.x);
 		}
-	}
+	});
 }
 
 // 3. sort: radix_sort_pairs() in sort.cu (one kernel per 8-bit pass, decoupled look-back)
