@@ -95,6 +95,8 @@ def lib():
                 "portablert_b200 has no CPU fallback.")
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in SYMBOLS.items():
+            if os.environ.get("PRT_B200_LIB_OLD_ABI") and not hasattr(L, name):
+                continue  # A/B runs against a library built from an older commit (tools/sweep.py)
             fn = getattr(L, name)  # AttributeError if the library lacks a declared symbol
             fn.restype = res
             fn.argtypes = args

@@ -11,16 +11,23 @@ namespace prt {
 constexpr int TRACE_THREADS = 128;
 // entries of the per-thread traversal stack kept in shared memory ([depth][thread]: conflict-free
 // whatever depth each lane is at); deeper entries overflow to a global buffer (rare)
+#ifndef PRT_BURST_UNROLL
+#define PRT_BURST_UNROLL 4
+#endif
 #ifndef PRT_SMEM_STACK
 #define PRT_SMEM_STACK 12
 #endif
 constexpr int SMEM_STACK = PRT_SMEM_STACK;
+constexpr int BURST_UNROLL = PRT_BURST_UNROLL;
 #ifndef PRT_MIN_BLOCKS
 #define PRT_MIN_BLOCKS 8
 #endif
 // node steps between two votes of the warp (leaf phase? enough lanes busy?)
 #ifndef PRT_NODE_BURST
 #define PRT_NODE_BURST 4
+#endif
+#ifndef PRT_SIMPLE_LOOP
+#define PRT_SIMPLE_LOOP 0
 #endif
 
 struct TraceParams {
@@ -467,9 +474,29 @@ __global__ void __launch_bounds__(TRACE_THREADS, PRT_MIN_BLOCKS) k_trace(const T
 			continue;
 		}
 
+#if PRT_SIMPLE_LOOP
+		// (A/B variant: every lane runs its own node-or-triangle loop, no phases, no votes)
+		if (has_ray) {
+			while (s.cur != PRT_DONE) {
+				if (at_node(s.cur))
+					trav_node_step<COUNT, FAST, W, WT>(s, stack, P.nodes, P.nodes4, r, fr);
+				else
+					trav_leaf_step<ANYHIT, WANT_UV, TRACK_PRIM, COUNT, FAST, WT>(s, stack, P.tris, r, opts, &wr,
+					                                                             my_idir, idir_stride);
+				if (!exhausted && __popc(__activemask()) < P.refill)
+					break;
+				if (COOP && exhausted && P.coop_after > 0 && ++tail_iters > 4 * P.coop_after) {
+					handover = true;
+					break;
+				}
+			}
+		}
+		__syncwarp();
+		handover = __any_sync(0xffffffffu, handover);
+#else
 		// ---- traverse until too few lanes are still busy
 		for (;;) {
-#pragma unroll
+#pragma unroll BURST_UNROLL
 			for (int k = 0; k < PRT_NODE_BURST; ++k) {
 				if (has_ray && at_node(s.cur)) {
 					trav_node_step<COUNT, FAST, W, WT>(s, stack, P.nodes, P.nodes4, r, fr);
@@ -497,6 +524,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PRT_MIN_BLOCKS) k_trace(const T
 					    s, stack, P.tris, r, opts, &wr, my_idir, idir_stride);
 			}
 		}
+#endif
 		// Hand the rays this warp is still tracing -- state and pending stack, one record each -- over
 		// to k_coop, which finishes every one of them with a whole warp (see k_coop above).
 		if (COOP && handover) {

@@ -84,7 +84,7 @@ def main():
             x = b.trace_dev(d_rays.data_ptr(), n, mask, **outs)
             if i >= 2:
                 ms.append(x)
-                km.append(b.last_kernel_ms)
+                km.append(b.last_kernel_ms if not os.environ.get('PRT_B200_LIB_OLD_ABI') else x)
         digest = bench.checksum(t if mask & 2 else None, pid if mask & 4 else None,
                                 valid if (mask & 16) and not (mask & 2) else None)
         if ref is None:
