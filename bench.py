@@ -344,8 +344,11 @@ def cxx_plugin_leg(w, rays, steps):
         tp, rp = os.path.join(tmp, "tris.bin"), os.path.join(tmp, "rays.bin")
         w["tris"].tofile(tp)
         rays[:n].tofile(rp)
-        out = subprocess.run([exe, tp, rp, str(w["mask"]), str(steps), "2"], capture_output=True,
-                             text=True, timeout=900)
+        # warm-up: enough calls for the library's lazy tree optimisation (after max(32 rays per
+        # triangle, 8 Mi rays)) and its first-use allocations to lie outside the timed calls
+        warm = 2 + int(np.ceil(max(32 * len(w["tris"]), 8 << 20) / max(1, n)))
+        out = subprocess.run([exe, tp, rp, str(w["mask"]), str(steps), str(min(warm, 12))],
+                             capture_output=True, text=True, timeout=900)
         lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
         if out.returncode != 0 or not lines:
             return {"unavailable": "bench_cxx failed: " + (out.stderr or out.stdout)[-300:]}
