@@ -26,6 +26,9 @@ constexpr int BURST_UNROLL = PRT_BURST_UNROLL;
 #ifndef PRT_NODE_BURST
 #define PRT_NODE_BURST 4
 #endif
+#ifndef PRT_LOCAL_STACK
+#define PRT_LOCAL_STACK 0
+#endif
 #ifndef PRT_SIMPLE_LOOP
 #define PRT_SIMPLE_LOOP 0
 #endif
@@ -391,12 +394,16 @@ __global__ void __launch_bounds__(TRACE_THREADS, PRT_MIN_BLOCKS) k_trace(const T
 		} // else: the list overflowed, every ray is traced again (same results)
 	}
 
+#if PRT_LOCAL_STACK
+	ArrayStack stack; // (A/B variant: the round-1 stack in local memory)
+#else
 	DevStack<W> stack;
 	stack.sm = s_stack + threadIdx.x;
 	stack.ovf = P.stack_ovf + ((size_t)blockIdx.x * TRACE_THREADS + threadIdx.x);
 	stack.stride = P.ovf_stride;
 	stack.pf_base = (W && P.prefetch) ? reinterpret_cast<const char *>(P.nodes4) : nullptr;
 	stack.sp = 0;
+#endif
 	const float *my_idir = FAST ? s_idir + threadIdx.x : nullptr; // (the exact kernels do not need it)
 	constexpr int idir_stride = TRACE_THREADS;
 	TravState s;

@@ -89,6 +89,9 @@ struct ArrayStack {
 	}
 	// several conditional pushes without a branch per entry: room(k) says that k more entries can
 	// be placed with put() at absolute positions (the device stack: inside its shared-memory part)
+#if defined(__CUDACC__)
+	PRT_HD uint2 peek(int k) const { return make_uint2(e[k].node, e[k].tmin_bits); }
+#endif
 	PRT_HD bool room(int) const { return true; }
 	PRT_HD void put(int at, bool pred, uint32_t node, uint32_t tmin_bits) {
 		if (pred) {
