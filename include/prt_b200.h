@@ -56,6 +56,12 @@ typedef struct {
 
 /* Traversal knobs (there is no other configuration channel in the reference API; the C++ backend
  * reads the same knobs from PRT_B200_* environment variables in init()). */
+/* Pruning is exact in real arithmetic; in binary32 it relies on the slack below covering the
+ * rounding of Moeller-Trumbore's t against the slab test of the boxes around the triangle.  That
+ * holds on every test of this repository, including needle / sliver triangles (aspect ratio up to
+ * 1e7) under grazing and edge-parallel rays (tests/test_emu_parity.py:
+ * test_pruning_on_slivers_and_grazing_rays), but it is an empirical bound, not a proof: prune = 0
+ * visits every box the line touches, exactly like the reference, for callers who need that. */
 typedef struct {
 	int prune;        /* 1 (default): cull subtrees whose entry distance exceeds the best hit so far
 	                     (+ slack); 0: visit every box the line touches, like bvh.hpp:224-265 */
