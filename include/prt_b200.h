@@ -236,6 +236,7 @@ float prt_b200_last_trace_ms(const prt_b200 *ctx);     /* device time of the las
 float prt_b200_last_kernel_ms(const prt_b200 *ctx);    /* ... of its traversal kernel alone (device entry points) */
 uint64_t prt_b200_exotic_rays(const prt_b200 *ctx);    /* rays traced by the exact second pass so far (device entry points) */
 uint64_t prt_b200_l2_bytes(const prt_b200 *ctx);       /* L2 cache size of the context's device */
+uint64_t prt_b200_graph_replays(const prt_b200 *ctx);  /* builds served by replaying the captured CUDA graph */
 /* Copies the built BVH back to the host for structural tests: nodes (64 B each), triangle records
  * (64 B each).  Either pointer may be NULL. */
 int prt_b200_download_bvh(const prt_b200 *ctx, void *nodes_out, void *tris_out);

@@ -73,6 +73,7 @@ SYMBOLS = {
     "prt_b200_last_kernel_ms": (C.c_float, [C.c_void_p]),
     "prt_b200_exotic_rays": (C.c_uint64, [C.c_void_p]),
     "prt_b200_l2_bytes": (C.c_uint64, [C.c_void_p]),
+    "prt_b200_graph_replays": (C.c_uint64, [C.c_void_p]),
     "prt_b200_download_bvh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "prt_b200_read_bandwidth": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
     "prt_b200_alloc_pinned": (C.c_void_p, [C.c_size_t]),

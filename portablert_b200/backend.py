@@ -289,6 +289,11 @@ class CUDABackend(Backend):
         return lib().prt_b200_exotic_rays(self._h)
 
     @property
+    def graph_replays(self):
+        """set_tris calls served by replaying the CUDA graph of the rebuild chain (small scenes)"""
+        return lib().prt_b200_graph_replays(self._h)
+
+    @property
     def l2_bytes(self):
         return lib().prt_b200_l2_bytes(self._h)
 

@@ -218,6 +218,8 @@ static int create_one(prt_b200 **out, int device) {
 		c->leaf_votes = std::max(1, std::min(32, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_COOP"))
 		c->coop_after = std::max(0, std::min(1 << 20, std::atoi(e)));
+	if (const char *e = std::getenv("PRT_B200_GRAPHS"))
+		c->use_graphs = std::atoi(e) != 0;
 	if (const char *e = std::getenv("PRT_B200_COOP_SP"))
 		c->coop_min_sp = std::max(0, std::min(64, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_COOP_BLOCKS"))
@@ -388,6 +390,8 @@ void prt_b200_destroy(prt_b200 *c) {
 			cudaStreamSynchronize(c->pipe_stream[k]);
 	if (c->stream)
 		cudaStreamSynchronize(c->stream);
+	if (c->build_graph)
+		cudaGraphExecDestroy(c->build_graph);
 	delete c->pool_in;
 	delete c->pool_out;
 	if (c->probe_host)
@@ -1045,7 +1049,11 @@ int prt_b200_nearest_hits(prt_b200 *c, const float *rays6, uint64_t n, uint32_t 
 	// A large pageable result (a fresh std::vector) is about to be touched for the first time by
 	// the staging threads: ask for transparent huge pages first (512x fewer page faults where the
 	// kernel allows it; harmless otherwise)
-	if ((size_t)n * layout->stride >= (size_t(16) << 20) && !is_pinned(hits_out, 1)) {
+	static const bool use_thp = [] {
+		const char *e = std::getenv("PRT_B200_THP");
+		return !e || std::atoi(e) != 0;
+	}();
+	if (use_thp && (size_t)n * layout->stride >= (size_t(16) << 20) && !is_pinned(hits_out, 1)) {
 		const uintptr_t lo = (reinterpret_cast<uintptr_t>(hits_out) + (2u << 20) - 1) & ~uintptr_t((2u << 20) - 1);
 		const uintptr_t hi = (reinterpret_cast<uintptr_t>(hits_out) + (size_t)n * layout->stride) &
 		                     ~uintptr_t((2u << 20) - 1);
@@ -1152,6 +1160,7 @@ float prt_b200_last_build_ms(const prt_b200 *c) { return c ? c->last_build_ms : 
 float prt_b200_last_trace_ms(const prt_b200 *c) { return c ? c->last_trace_ms : 0.f; }
 float prt_b200_last_kernel_ms(const prt_b200 *c) { return c ? c->last_kernel_ms : 0.f; }
 uint64_t prt_b200_exotic_rays(const prt_b200 *c) { return c ? c->exotic_rays : 0; }
+uint64_t prt_b200_graph_replays(const prt_b200 *c) { return c ? c->graph_replays : 0; }
 uint64_t prt_b200_l2_bytes(const prt_b200 *c) { return c ? c->l2_bytes : 0; }
 
 int prt_b200_download_bvh(const prt_b200 *cc, void *nodes_out, void *tris_out) {

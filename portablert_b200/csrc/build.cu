@@ -15,6 +15,7 @@
 // DESIGN.md (build roofline).
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "prt_ctx.h"
 #include "prt_treelet.cuh"
@@ -1053,34 +1054,91 @@ int build_lbvh(prt_b200 *c, const float *d_tris9, uint64_t n) {
 	const int stream_grid = (int)std::min<uint64_t>((n + TT - 1) / TT, (uint64_t)c->sm_count * 8);
 	const int bits = morton_bits_for(n);
 	c->morton_bits = bits;
-
-	k_bounds_init<<<1, 32, 0, s>>>(c->bounds.as<uint32_t>());
-	k_bounds<<<stream_grid, TT, 0, s>>>(d_tris9, n, c->bounds.as<uint32_t>());
-	k_morton<<<stream_grid, TT, 0, s>>>(d_tris9, n, c->bounds.as<uint32_t>(), bits,
-	                                    c->keys[0].as<uint64_t>(), c->vals[0].as<uint32_t>());
-	c->launches += 3;
-
-	int cur = 0;
-	if (n > 1) {
-		uint64_t *const kk[2] = {c->keys[0].as<uint64_t>(), c->keys[1].as<uint64_t>()};
-		uint32_t *const vv[2] = {c->vals[0].as<uint32_t>(), c->vals[1].as<uint32_t>()};
-		if (int rc = radix_sort_pairs(c, c->sort_scratch, kk, vv, n, 3 * bits, s, &cur))
-			return rc;
-	}
-
 	const int g = (int)((n + 255) / 256);
-	if (n == 1) {
-		k_leaves<<<1, 256, 0, s>>>(d_tris9, c->vals[cur].as<uint32_t>(), n, c->trirecs.as<TriRec>(),
-		                           c->leaf_box.as<float4>(), vf);
-		k_single<<<1, 1, 0, s>>>(c->nodes.as<Node>(), c->trirecs.as<TriRec>(), c->leaf_box.as<float4>(),
-		                         c->root_info.as<RootInfo>());
-		c->launches += 2;
+
+	// everything from the centroid bounds to the hierarchy: ~11 dependent launches and memsets
+	auto enqueue = [&](int *cur_out) -> int {
+		k_bounds_init<<<1, 32, 0, s>>>(c->bounds.as<uint32_t>());
+		k_bounds<<<stream_grid, TT, 0, s>>>(d_tris9, n, c->bounds.as<uint32_t>());
+		k_morton<<<stream_grid, TT, 0, s>>>(d_tris9, n, c->bounds.as<uint32_t>(), bits,
+		                                    c->keys[0].as<uint64_t>(), c->vals[0].as<uint32_t>());
+		c->launches += 3;
+		int cur = 0;
+		if (n > 1) {
+			uint64_t *const kk[2] = {c->keys[0].as<uint64_t>(), c->keys[1].as<uint64_t>()};
+			uint32_t *const vv[2] = {c->vals[0].as<uint32_t>(), c->vals[1].as<uint32_t>()};
+			if (int rc = radix_sort_pairs(c, c->sort_scratch, kk, vv, n, 3 * bits, s, &cur))
+				return rc;
+		}
+		if (n == 1) {
+			k_leaves<<<1, 256, 0, s>>>(d_tris9, c->vals[cur].as<uint32_t>(), n, c->trirecs.as<TriRec>(),
+			                           c->leaf_box.as<float4>(), vf);
+			k_single<<<1, 1, 0, s>>>(c->nodes.as<Node>(), c->trirecs.as<TriRec>(), c->leaf_box.as<float4>(),
+			                         c->root_info.as<RootInfo>());
+			c->launches += 2;
+		} else {
+			PRT_CUDA(c, cudaMemsetAsync(c->bound.p, 0xff, (n - 1) * 4, s));
+			k_hierarchy<<<g, 256, 0, s>>>(d_tris9, c->vals[cur].as<uint32_t>(), c->keys[cur].as<uint64_t>(),
+			                              (int)n, c->trirecs.as<TriRec>(), c->nodes.as<Node>(),
+			                              c->bound.as<int>(), c->root_info.as<RootInfo>(), vf);
+			c->launches += 1;
+		}
+		*cur_out = cur;
+		return PRT_OK;
+	};
+
+	// Small scenes are bound by the latency of that launch chain (69 k triangles: 0.13 ms for ~50 us of
+	// kernels).  A scene family that is rebuilt from the same buffers -- same triangle pointer and
+	// count, scratch not reallocated in between -- therefore gets its chain captured into a CUDA graph
+	// at the second build and replayed with one launch from the third on (env PRT_B200_GRAPHS=0: off).
+	struct Key {
+		const void *p[12];
+		uint64_t n;
+		int bits, vf;
+	} key{};
+	const void *ptrs[12] = {d_tris9,         c->nodes.p,    c->trirecs.p,      c->keys[0].p, c->keys[1].p,
+	                        c->vals[0].p,    c->vals[1].p,  c->sort_scratch.p, c->bounds.p,  c->bound.p,
+	                        c->root_info.p,  c->leaf_box.p};
+	for (int k = 0; k < 12; ++k)
+		key.p[k] = ptrs[k];
+	key.n = n;
+	key.bits = bits;
+	key.vf = vf ? 1 : 0;
+	static_assert(sizeof(Key) <= sizeof(c->build_graph_key), "graph key storage");
+	int cur = 0;
+	const bool graphable = c->use_graphs && n > 1 && n <= (1ull << 20);
+	if (graphable && c->build_graph && std::memcmp(&key, c->build_graph_key, sizeof key) == 0) {
+		PRT_CUDA(c, cudaGraphLaunch(c->build_graph, s));
+		c->launches += c->build_graph_launches;
+		c->graph_replays++;
+	} else if (graphable && c->build_seen && std::memcmp(&key, c->build_seen_key, sizeof key) == 0) {
+		const uint64_t l0 = c->launches;
+		PRT_CUDA(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+		const int rc = enqueue(&cur);
+		cudaGraph_t graph = nullptr;
+		const cudaError_t e = cudaStreamEndCapture(s, &graph);
+		cudaGraphExec_t exec = nullptr;
+		if (rc == PRT_OK && e == cudaSuccess && graph &&
+		    cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+			if (c->build_graph)
+				cudaGraphExecDestroy(c->build_graph);
+			c->build_graph = exec;
+			std::memcpy(c->build_graph_key, &key, sizeof key);
+			c->build_graph_launches = (int)(c->launches - l0);
+			PRT_CUDA(c, cudaGraphLaunch(exec, s));
+		} else { // capture not possible: run the chain directly
+			cudaGetLastError();
+			c->launches = l0;
+			if (int rc2 = enqueue(&cur))
+				return rc2;
+		}
+		if (graph)
+			cudaGraphDestroy(graph);
 	} else {
-		PRT_CUDA(c, cudaMemsetAsync(c->bound.p, 0xff, (n - 1) * 4, s));
-		k_hierarchy<<<g, 256, 0, s>>>(d_tris9, c->vals[cur].as<uint32_t>(), c->keys[cur].as<uint64_t>(),
-		                              (int)n, c->trirecs.as<TriRec>(), c->nodes.as<Node>(),
-		                              c->bound.as<int>(), c->root_info.as<RootInfo>(), vf);
-		c->launches += 1;
+		if (int rc = enqueue(&cur))
+			return rc;
+		std::memcpy(c->build_seen_key, &key, sizeof key);
+		c->build_seen = true;
 	}
 	if (c->optimise_mode == 1) // inside every set_tris
 		if (int rc = optimise_tree(c, s))

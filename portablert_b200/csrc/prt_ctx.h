@@ -149,6 +149,13 @@ struct prt_b200 {
 	uint32_t exotic_mask = 0;
 	uint64_t exotic_rays = 0; // rays traced by the exact pass so far
 	int morton_bits = 0;      // bits per axis of the current tree's Morton keys
+	// CUDA graph of the rebuild chain of a small scene family (build.cu: build_lbvh)
+	cudaGraphExec_t build_graph = nullptr;
+	alignas(8) unsigned char build_graph_key[128] = {}, build_seen_key[128] = {};
+	bool build_seen = false;
+	int build_graph_launches = 0;
+	int use_graphs = 1;       // env PRT_B200_GRAPHS
+	uint64_t graph_replays = 0;
 	// ray reordering scratch, one set per launch slot (concurrent launches on different streams)
 	struct RaySort {
 		prt::DevBuf keys[2], vals[2], scratch;

@@ -270,3 +270,38 @@ def test_process_per_gpu_sharding_over_nccl():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "SHARDING_OK" in out.stdout, out.stdout[-2000:]
+
+
+def test_rebuild_chain_is_replayed_from_a_cuda_graph(cuda):
+    """Small scenes: the ~11 launches of a rebuild are captured into a CUDA graph at the second build
+    from the same buffers and replayed afterwards.  Every build must produce the same BVH bytes, a
+    different scene in between must not be served from the stale graph, and tracing still works."""
+    import torch
+    dev = torch.device("cuda", 0)
+    a = torch.from_numpy(scenes.blob(96, 96)).to(dev)
+    b_host = scenes.blob(96, 96, radius=0.13, bump=0.3)
+    b = torch.from_numpy(b_host).to(dev)
+    rays = scenes.pinhole_rays(320, 200)
+    torch.cuda.synchronize()
+    cuda.set_tree_optimisation(0)
+    before = cuda.graph_replays
+    want = None
+    for k in range(5):
+        cuda.set_tris_dev(a.data_ptr(), len(a))
+        nodes, recs = cuda.download_bvh()
+        if want is None:
+            want = (nodes.tobytes(), recs.tobytes(), cuda.nearest_hits(rays).copy())
+        assert nodes.tobytes() == want[0] and recs.tobytes() == want[1], k
+    assert cuda.graph_replays >= before + 2, "builds 3.. must be graph replays"
+    cuda.set_tris_dev(b.data_ptr(), len(b))  # same size, other buffer: not the captured chain
+    other = cuda.nearest_hits(rays)
+    fresh = fresh_backend({"PRT_B200_GRAPHS": "0"})
+    try:
+        fresh.set_tree_optimisation(0)
+        fresh.set_tris(b_host)
+        assert same_hits(other, fresh.nearest_hits(rays))
+    finally:
+        fresh.shutdown()
+    cuda.set_tris_dev(a.data_ptr(), len(a))
+    assert same_hits(cuda.nearest_hits(rays), want[2])
+    cuda.set_tree_optimisation(3)
