@@ -224,8 +224,6 @@ static int create_one(prt_b200 **out, int device) {
 		c->coop_min_sp = std::max(0, std::min(64, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_COOP_BLOCKS"))
 		c->coop_blocks = std::max(1, std::min(8, std::atoi(e)));
-	if (const char *e = std::getenv("PRT_B200_PREFETCH"))
-		c->prefetch = std::max(0, std::min(2, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_COPY_THREADS"))
 		c->copy_threads = std::max(1, std::min(32, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_BCAST"))

@@ -179,7 +179,6 @@ struct prt_b200 {
 	int refill = 16;                         // env PRT_B200_REFILL: dynamic ray-fetch threshold (lanes), binary-node kernels
 	int refill_wide = 24;                    // env PRT_B200_REFILL_WIDE: ... of the wide-node kernels (incoherent rays: measured +3.5 %)
 	int leaf_votes = 8;                      // env PRT_B200_LEAF_VOTES: lanes waiting at a triangle that start a leaf phase
-	int prefetch = 2;                        // env PRT_B200_PREFETCH: 0 never, 1 always, 2 when the BVH exceeds L2
 	bool packed_d2h = true;                  // env PRT_B200_PACKED_D2H: pageable results come back tightly packed
 	int chunk_log2 = 0; // host entry point: rays per pipeline chunk (0 = automatic)
 	bool pipe_trace = false; // env PRT_B200_PIPE_TRACE: print the stage timeline of every host call

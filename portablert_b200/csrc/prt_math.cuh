@@ -91,14 +91,15 @@ struct Box {
 // TriRec, so results cannot change.  Wide node i describes the subtree of binary node i (same
 // numbering, no allocation pass); only every other level is ever reached from the root.
 //   child >= 0 internal (wide/binary node index), < 0 leaf ~triangle record, PRT_NO_CHILD empty
+// (The three scales are stored as whole floats -- the record has the room -- so that the traversal
+// spends one multiplication per axis on them instead of unpacking exponent bytes.)
 struct __attribute__((aligned(16))) Node4 {
 	float p[3];
-	uint8_t e[3]; // biased exponents: scale[a] = 2^(e[a] - 127)
-	uint8_t pad0;
+	float scale_x;     // power of two
 	uint8_t qlo[3][4]; // [axis][child]
 	uint8_t qhi[3][4];
 	int32_t child[4];
-	uint32_t pad1[2];
+	float scale_y, scale_z;
 };
 static_assert(sizeof(Node4) == 64, "Node4 must be 64 bytes");
 
@@ -145,11 +146,11 @@ PRT_HD Node4 make_node4(const WideChild *ch, int count) {
 			eb = 1;
 		if (eb > 254 || !(ext < INFINITY))
 			eb = 254;
-		nd.e[a] = (uint8_t)eb;
 		scale[a] = pow2_from_biased((uint32_t)eb);
 	}
-	nd.pad0 = 0;
-	nd.pad1[0] = nd.pad1[1] = 0;
+	nd.scale_x = scale[0];
+	nd.scale_y = scale[1];
+	nd.scale_z = scale[2];
 	for (int k = 0; k < 4; ++k) {
 		if (k < count) {
 			nd.child[k] = ch[k].ref;

@@ -29,6 +29,9 @@ constexpr int BURST_UNROLL = PRT_BURST_UNROLL;
 #ifndef PRT_LOCAL_STACK
 #define PRT_LOCAL_STACK 0
 #endif
+#ifndef PRT_LEAF_PREFETCH
+#define PRT_LEAF_PREFETCH 0
+#endif
 #ifndef PRT_SIMPLE_LOOP
 #define PRT_SIMPLE_LOOP 0
 #endif
@@ -56,7 +59,6 @@ struct TraceParams {
 	float scene_absmax[3];
 	int refill;     // re-fetch rays when fewer than this many lanes of a warp are still traversing
 	int leaf_votes; // a leaf phase starts when leaf_votes/32 of the busy lanes wait at a triangle
-	int prefetch;   // 1: L2-prefetch nodes as they are pushed (scenes larger than L2)
 	int rays_vec;   // the ray buffer is 8-byte aligned: three 8-byte loads per ray
 	int32_t root;         // index of the root node
 	const uint32_t *perm; // ray processing order (reordered batches) or nullptr = identity
@@ -84,13 +86,12 @@ struct TraceParams {
 constexpr int COOP_PARK = 16; // words of a parked ray state
 
 // Per-thread stack: SMEM_STACK entries in shared memory, the rest in global memory.
-// PF (the wide-node kernels, i.e. scenes that do not fit L2): nodes are prefetched into L2 as they
-// are pushed -- most pushed subtrees of an incoherent ray are visited later.
-template <bool PF> struct DevStack {
+// (An L2 prefetch of every pushed node -- most pushed subtrees of an incoherent ray are visited
+// later -- measured +-1 % on C4 and cost six instructions per entry in divergent code: removed.)
+struct DevStack {
 	uint2 *sm;  // &block_stack[threadIdx.x], entry k at sm[k * TRACE_THREADS]
 	uint2 *ovf; // &overflow[global thread], entry k at ovf[k * stride]
 	uint32_t stride;
-	const char *pf_base; // PF: node array, or nullptr = off
 	int sp;
 	__device__ __forceinline__ void push(uint32_t node, uint32_t tmin_bits) {
 		if (sp < SMEM_STACK)
@@ -98,8 +99,6 @@ template <bool PF> struct DevStack {
 		else
 			ovf[(size_t)(sp - SMEM_STACK) * stride] = make_uint2(node, tmin_bits);
 		++sp;
-		if (PF && pf_base && (int32_t)node >= 0)
-			asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_base + (size_t)node * 64));
 	}
 	__device__ __forceinline__ void pop(uint32_t &node, uint32_t &tmin_bits) {
 		--sp;
@@ -107,16 +106,32 @@ template <bool PF> struct DevStack {
 		node = e.x;
 		tmin_bits = e.y;
 	}
+	// The next entry the best hit so far does not rule out, or PRT_DONE.  Entries in the overflow
+	// first (rare), then a loop over the shared part alone: no per-iteration "where does it live".
+	__device__ __forceinline__ uint32_t pop_live(float limit) {
+		while (sp > SMEM_STACK) {
+			--sp;
+			const uint2 e = ovf[(size_t)(sp - SMEM_STACK) * stride];
+			if (!(__uint_as_float(e.y) > limit))
+				return e.x;
+		}
+		const uint2 *p = sm + sp * TRACE_THREADS;
+		while (sp > 0) {
+			--sp;
+			p -= TRACE_THREADS;
+			const uint2 e = *p;
+			if (!(__uint_as_float(e.y) > limit))
+				return e.x;
+		}
+		return (uint32_t)PRT_DONE;
+	}
 	__device__ __forceinline__ uint2 peek(int k) const { // entry k from the bottom
 		return k < SMEM_STACK ? sm[k * TRACE_THREADS] : ovf[(size_t)(k - SMEM_STACK) * stride];
 	}
 	__device__ __forceinline__ bool room(int k) const { return sp + k <= SMEM_STACK; }
 	__device__ __forceinline__ void put(int at, bool pred, uint32_t node, uint32_t tmin_bits) {
-		if (pred) { // (a predicated store: no divergent region per entry)
+		if (pred) // (a predicated store: no divergent region per entry)
 			sm[at * TRACE_THREADS] = make_uint2(node, tmin_bits);
-			if (PF && pf_base && (int32_t)node >= 0)
-				asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_base + (size_t)node * 64));
-		}
 	}
 };
 
@@ -397,11 +412,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, PRT_MIN_BLOCKS) k_trace(const T
 #if PRT_LOCAL_STACK
 	ArrayStack stack; // (A/B variant: the round-1 stack in local memory)
 #else
-	DevStack<W> stack;
+	DevStack stack;
 	stack.sm = s_stack + threadIdx.x;
 	stack.ovf = P.stack_ovf + ((size_t)blockIdx.x * TRACE_THREADS + threadIdx.x);
 	stack.stride = P.ovf_stride;
-	stack.pf_base = (W && P.prefetch) ? reinterpret_cast<const char *>(P.nodes4) : nullptr;
 	stack.sp = 0;
 #endif
 	const float *my_idir = FAST ? s_idir + threadIdx.x : nullptr; // (the exact kernels do not need it)
@@ -507,8 +521,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, PRT_MIN_BLOCKS) k_trace(const T
 			for (int k = 0; k < PRT_NODE_BURST; ++k) {
 				if (has_ray && at_node(s.cur)) {
 					trav_node_step<COUNT, FAST, W, WT>(s, stack, P.nodes, P.nodes4, r, fr);
-					if (s.cur < 0) // parked at a triangle: have its record on the way
-						asm volatile("prefetch.global.L1 [%0];" ::"l"(P.tris + (uint32_t)(~s.cur)));
+#if PRT_LEAF_PREFETCH
+					// (A/B variant: a lane parked at a triangle has its record prefetched into L1.  Measured
+					// 4-7 % SLOWER on C2/C3/C3B/C5: the address arithmetic runs on every node step.)
+					if (!W && s.cur < 0)
+						asm volatile("prefetch.global.L1 [%0];" ::"l"(
+						    reinterpret_cast<const char *>(P.tris) + ((uint64_t)(uint32_t)(~s.cur) << 6)));
+#endif
 				}
 			}
 			const bool leaf = has_ray && s.cur < 0;

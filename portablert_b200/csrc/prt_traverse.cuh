@@ -33,6 +33,11 @@ __device__ __forceinline__ Vec4 ld16(const void *p) {
 // 32 bytes with ONE instruction: sm_100 has 256-bit global loads (LDG.E.ENL2.256); a 64-byte node
 // or triangle record is two L1 lookups instead of four
 __device__ __forceinline__ void ld32(const void *p, Vec4 &a, Vec4 &b) {
+#if defined(PRT_LD128) // (A/B variant: two 128-bit loads)
+	a = ld16(p);
+	b = ld16(static_cast<const char *>(p) + 16);
+	return;
+#endif
 	asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 	             : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
 	             : "l"(p));
@@ -86,6 +91,15 @@ struct ArrayStack {
 		--sp;
 		node = e[sp].node;
 		tmin_bits = e[sp].tmin_bits;
+	}
+	// the next entry whose entry distance does not exceed `limit`, or PRT_DONE (stack empty)
+	PRT_HD uint32_t pop_live(float limit) {
+		while (sp > 0) {
+			--sp;
+			if (!(u2f(e[sp].tmin_bits) > limit))
+				return e[sp].node;
+		}
+		return 0x7fffffffu;
 	}
 	// several conditional pushes without a branch per entry: room(k) says that k more entries can
 	// be placed with put() at absolute positions (the device stack: inside its shared-memory part)
@@ -236,15 +250,7 @@ PRT_HD void trav_init(TravState &s, const RayC &r, const TraverseOpts &opt, uint
 
 // Pop: the next stacked subtree that the best hit so far does not rule out, or PRT_DONE.
 template <class STK> PRT_HD void trav_pop(TravState &s, STK &stack) {
-	s.cur = PRT_DONE;
-	while (stack.sp > 0) {
-		uint32_t node, tb;
-		stack.pop(node, tb);
-		if (!(u2f(tb) > s.limit)) {
-			s.cur = (int32_t)node;
-			break;
-		}
-	}
+	s.cur = (int32_t)stack.pop_live(s.limit);
 }
 
 // One step through a compressed 4-wide node (fast rays only): dequantise the four child boxes
@@ -257,7 +263,7 @@ PRT_HD bool wide_node_step(TravState &s, STK &stack, const Node4 *nodes4, const 
 	Vec4 v0, v1, v2, v3;
 	ld32(np, v0, v1);
 	ld32(np + 32, v2, v3);
-	const uint32_t ebits = f2u(v0.w);
+	const float scale[3] = {v0.w, v3.z, v3.w};
 	const uint32_t qw[6] = {f2u(v1.x), f2u(v1.y), f2u(v1.z), f2u(v1.w), f2u(v2.x), f2u(v2.y)};
 	const int32_t ch[4] = {(int32_t)f2u(v2.z), (int32_t)f2u(v2.w), (int32_t)f2u(v3.x),
 	                       (int32_t)f2u(v3.y)};
@@ -267,7 +273,7 @@ PRT_HD bool wide_node_step(TravState &s, STK &stack, const Node4 *nodes4, const 
 #pragma unroll
 	for (int a = 0; a < 3; ++a) {
 		const bool neg = fr.idir[a] < 0.0f;
-		sc[a] = fmul(pow2_from_biased((ebits >> (8 * a)) & 0xffu), fr.idir[a]);
+		sc[a] = fmul(scale[a], fr.idir[a]);
 		bn[a] = PRT_FMA(pp[a], fr.idir[a], fr.cn[a]);
 		bf[a] = PRT_FMA(pp[a], fr.idir[a], fr.cf[a]);
 		qn[a] = neg ? qw[3 + a] : qw[a];

@@ -336,9 +336,6 @@ int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, c
 		c->wide_batches++;
 		P.refill = c->refill_wide;
 	}
-	// nodes pushed on the stack are prefetched into L2 when the tree cannot live there
-	const uint64_t tree_bytes = c->n_nodes * 64 + c->n_tris * 64;
-	P.prefetch = c->prefetch == 1 || (c->prefetch == 2 && c->l2_bytes && tree_bytes > c->l2_bytes);
 
 	if (d_counts) { // instrumented run: set-aside rays (if any) count as zero
 		PRT_CUDA(c, cudaMemsetAsync(d_counts, 0, n * 8, s));
@@ -375,7 +372,6 @@ int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, c
 	// ---- exact pass over the set-aside rays
 	P.slow_count = P.counter + 3;
 	P.slow_host = nullptr;
-	P.prefetch = 0;
 	static_assert(sizeof(TraceParams) <= sizeof(c->exotic_blob), "exotic_blob too small");
 	std::memcpy(c->exotic_blob, &P, sizeof P);
 	const KernelFn exact_fn = wt ? trace_kernel_wt_exact(mask, aos) : trace_kernel_exact(mask, aos);

@@ -206,7 +206,8 @@ def test_wide_node_boxes_contain_their_children(emu):
     for i in range(0, len(nodes), 7):
         w = wide[i]
         p = w[0:12].copy().view(np.float32)
-        scale = np.ldexp(1.0, w[12:15].astype(np.int64) - 127)
+        scale = np.concatenate([w[12:16], w[56:64]]).copy().view(np.float32).astype(np.float64)
+        assert (np.frexp(scale)[0] == 0.5).all()  # powers of two
         qlo = w[16:28].reshape(3, 4).astype(np.float64)
         qhi = w[28:40].reshape(3, 4).astype(np.float64)
         child = w[40:56].copy().view(np.int32)

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--tag", default="")
     ap.add_argument("--repeat", type=int, default=1, help="trace the batch tiled this many times")
+    ap.add_argument("--passes", default="2", help="treelet passes, comma-separated list to sweep")
     args = ap.parse_args()
     import torch
 
@@ -64,18 +65,18 @@ def main():
                 pid=pid.data_ptr() if mask & 4 else 0, p=p.data_ptr() if mask & 8 else 0,
                 valid=valid.data_ptr() if mask & 16 else 0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    names, values = [], []
+    names, values = ["passes"], [args.passes.split(",")]
     for s in args.set:
         k, v = s.split("=")
         names.append(k)
         values.append(v.split(","))
     ref = None
-    for combo in itertools.product(*values) if names else [()]:
-        for k, v in zip(names, combo):
+    for combo in itertools.product(*values):
+        for k, v in zip(names[1:], combo[1:]):
             os.environ["PRT_B200_" + k] = v
         b = prt.CUDABackend(device=0)
         b.init()
-        b.set_tree_optimisation(1, 2)  # optimised inside set_tris: steady state of a static scene
+        b.set_tree_optimisation(1, int(combo[0]))  # optimised inside set_tris: steady state of a static scene
         build = b.set_tris_dev(d_tris.data_ptr(), len(tris))
         ms, km = [], []
         for i in range(2 + args.steps):
