@@ -211,11 +211,15 @@ static int create_one(prt_b200 **out, int device) {
 	if (const char *e = std::getenv("PRT_B200_CHUNK_LOG2"))
 		c->chunk_log2 = std::max(10, std::min(24, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_REFILL"))
-		c->refill = c->refill_wide = std::max(0, std::min(32, std::atoi(e)));
+		c->refill = c->refill_wide = c->refill_scattered = std::max(0, std::min(32, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_REFILL_WIDE"))
 		c->refill_wide = std::max(0, std::min(32, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_LEAF_VOTES"))
-		c->leaf_votes = std::max(1, std::min(32, std::atoi(e)));
+		c->leaf_votes = c->leaf_votes_wide = std::max(1, std::min(32, std::atoi(e)));
+	if (const char *e = std::getenv("PRT_B200_LEAF_VOTES_WIDE"))
+		c->leaf_votes_wide = std::max(1, std::min(32, std::atoi(e)));
+	if (const char *e = std::getenv("PRT_B200_REFILL_SCATTERED"))
+		c->refill_scattered = std::max(0, std::min(32, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_COOP"))
 		c->coop_after = std::max(0, std::min(1 << 20, std::atoi(e)));
 	if (const char *e = std::getenv("PRT_B200_GRAPHS"))

@@ -1014,8 +1014,8 @@ static int morton_bits_for(uint64_t n) {
 	// for these benchmarks; every 8 key bits cost one more sort pass.
 	if (n <= (1ull << 16))
 		return 10; // 30-bit keys, 4 passes
-	if (n <= (1ull << 22))
-		return 13; // 39-bit keys, 5 passes
+	if (n <= (1ull << 24))
+		return 13; // 39-bit keys, 5 passes (8192 cells per axis; C4's 10 M triangles: same nodes/ray as 16)
 	return 16;     // 48-bit keys, 6 passes (PRT_B200_MORTON_BITS=21: 63-bit keys, 8 passes)
 }
 

@@ -140,7 +140,7 @@ struct prt_b200 {
 	const void *coop_seen[2] = {nullptr, nullptr};
 	int coop_min_sp = 0;      // env PRT_B200_COOP_SP: ... for rays with at least this many stacked subtrees
 	int coop_blocks = 4;      // env PRT_B200_COOP_BLOCKS: blocks per SM of the follow-up kernel
-	int coop_after = 8;       // env PRT_B200_COOP: iterations past the end of the batch before a warp goes cooperative (0 = never)
+	int coop_after = 4;       // env PRT_B200_COOP: iterations past the end of the batch before a warp goes cooperative (0 = never)
 	// the exact pass of the last EXOTIC_DEFERRED launch (trace.cu: finish_exotic)
 	bool pending_exotic = false;
 	alignas(16) unsigned char exotic_blob[384] = {}; // its TraceParams
@@ -177,7 +177,9 @@ struct prt_b200 {
 	bool recs_vertex_form = false;           // the current triangle records hold v1, v2 (watertight) instead of the edges
 	int fast_boxes = 1;                      // env PRT_B200_FAST_BOXES=0 forces the exact test everywhere
 	int refill = 16;                         // env PRT_B200_REFILL: dynamic ray-fetch threshold (lanes), binary-node kernels
+	int refill_scattered = 8;                // env PRT_B200_REFILL_SCATTERED: ... for reordered batches and trees beyond half of L2 (C3B +1.6 %, C5 +4.8 %)
 	int refill_wide = 24;                    // env PRT_B200_REFILL_WIDE: ... of the wide-node kernels (incoherent rays: measured +3.5 %)
+	int leaf_votes_wide = 4;                 // env PRT_B200_LEAF_VOTES_WIDE: ... in the wide-node kernels (C4 +2.3 % over 8)
 	int leaf_votes = 8;                      // env PRT_B200_LEAF_VOTES: lanes waiting at a triangle that start a leaf phase
 	bool packed_d2h = true;                  // env PRT_B200_PACKED_D2H: pageable results come back tightly packed
 	int chunk_log2 = 0; // host entry point: rays per pipeline chunk (0 = automatic)

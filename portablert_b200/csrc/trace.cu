@@ -335,6 +335,11 @@ int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, c
 	if (wide) {
 		c->wide_batches++;
 		P.refill = c->refill_wide;
+		P.leaf_votes = c->leaf_votes_wide;
+	} else if (P.perm || (c->l2_bytes && (c->n_nodes + c->n_tris) * 64 * 2 > c->l2_bytes)) {
+		// scattered fetches (a reordered batch, or a tree that does not sit comfortably in L2):
+		// refilling less often measured better than keeping the warps fuller
+		P.refill = c->refill_scattered;
 	}
 
 	if (d_counts) { // instrumented run: set-aside rays (if any) count as zero
