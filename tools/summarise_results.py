@@ -13,6 +13,13 @@ R1 = {"c2": 6782, "c3": 11263, "c3b": 5381, "c5": 5834, "c4": 2459}  # profiles/
 R1_E2E = {"c2": 1264, "c3": 1433, "c3b": 1866, "c5": 1751, "c4": 1080}
 
 
+TRAFFIC = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+try:
+    HBM_PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    HBM_PEAK = 6535.4
+
+
 def load(name):
     p = os.path.join(G, name)
     if not os.path.exists(p):
@@ -43,6 +50,8 @@ def main():
         par = (f"{p.get('checked_rays', 0):,} / {p.get('valid_mismatch')} / {p.get('pid_mismatch')} / "
                f"{p.get('pid_ties')} / {p.get('t_bitexact')}") if p else "-"
         dram = r.get("dram_frac_of_hbm")
+        if TRAFFIC.get(cfg) and r.get("kernel_ms"):  # the committed capture of THIS build
+            dram = TRAFFIC[cfg]["dram_bytes"] / (r["kernel_ms"] * 1e-3) / 1e9 / HBM_PEAK
         out.append(f"| {cfg.upper()} | {d['config']['tris']:,} | {d['config']['rays']:,} | "
                    f"mask {d['config']['tag_mask']} | {d['ms_per_step']:.3f} | **{d['value']:.0f}** | {R1[cfg]} | "
                    f"{r['kernel_ms']:.3f} | {r['nodes_per_ray']:.1f} | {r['tris_per_ray']:.2f} | "
@@ -57,7 +66,7 @@ def main():
                    f"{r['peak'] if r['bound'] == 'hbm' else '-'} GB/s ({r['peak_source']}); measured on the box in "
                    f"the same run: L2 read {r['l2_read_gbs_measured']:.0f} GB/s, HBM read "
                    f"{r['hbm_read_gbs_measured']:.0f} GB/s.  ncu (profiles/r02_trace_c4_full.md): "
-                   f"{(r.get('traffic') or 0) / 1e9:.1f} GB of DRAM traffic per launch.  Clocks during the timed "
+                   f"{(TRAFFIC.get('c4', {}).get('dram_bytes') or r.get('traffic') or 0) / 1e9:.1f} GB of DRAM traffic per launch.  Clocks during the timed "
                    f"region: {d['clocks']}.\n")
         if "value" in c:
             out.append(f"CPU reference beside it (unmodified reference CPU backend, oracle/_ref): "
