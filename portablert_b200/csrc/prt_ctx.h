@@ -163,7 +163,7 @@ struct prt_b200 {
 	prt::DevBuf probe_ticket;                    // 2 x u64 block tickets of the coherence probe
 	unsigned long long *probe_host = nullptr;    // 2 x u64 mapped pinned flags (host view)
 	unsigned long long *probe_dev = nullptr;     // ... and their device view
-	int ray_key_ob = 4, ray_key_db = 4; // sort key bits per axis: origin, direction (env PRT_B200_RAYKEY="ob,db")
+	int ray_key_ob = 3, ray_key_db = 2; // sort key bits per axis: origin, direction (env PRT_B200_RAYKEY="ob,db"): 15 bits = 2 passes
 	int sort_rays = 2; // env PRT_B200_SORT_RAYS: 0 never, 1 always, 2 auto (only incoherent batches)
 	float scene_lo[3] = {0.f, 0.f, 0.f}, scene_hi[3] = {0.f, 0.f, 0.f};
 	uint64_t sorted_batches = 0, unsorted_batches = 0, wide_batches = 0;
@@ -240,8 +240,10 @@ int host_ray_probe(const prt_b200 *c, const float *rays6, uint64_t n);
 // sort.cu
 int radix_sort_pairs(prt_b200 *c, DevBuf &scratch, uint64_t *const keys[2], uint32_t *const vals[2],
                      uint64_t n, int key_bits, cudaStream_t s, int *result_index);
-int radix_sort_pairs32(prt_b200 *c, DevBuf &scratch, uint32_t *const keys[2], uint32_t *const vals[2],
-                       uint64_t n, int key_bits, cudaStream_t s, int *result_index);
+int radix_sort_prepare32(prt_b200 *c, DevBuf &scratch, uint64_t n, int key_bits, cudaStream_t s,
+                         uint32_t **ghist, int *passes);
+int radix_sort_run32_identity(prt_b200 *c, DevBuf &scratch, uint32_t *const keys[2], uint32_t *const vals[2],
+                              uint64_t n, int key_bits, cudaStream_t s, int *result_index);
 
 int launch_read_probe(prt_b200 *c, const void *buf, uint64_t bytes, int iters, float *ms);
 

@@ -128,7 +128,8 @@ __global__ void __launch_bounds__(SO_THREADS)
 		const int pos = wbase + k * 32 + lane;
 		const bool ok = pos < tile_cnt;
 		key[k] = ok ? keys_in[tile_base + pos] : (K)~(K)0;
-		val[k] = ok ? vals_in[tile_base + pos] : 0u;
+		// (vals_in == nullptr: the first pass of a sort whose values are the positions 0..n-1)
+		val[k] = ok ? (vals_in ? vals_in[tile_base + pos] : (uint32_t)(tile_base + pos)) : 0u;
 	}
 	// ---- early counts: warp-private digit histograms, so that the tile's counts can be published
 	// (and the successors' look-back can proceed) before the slower ranking below
@@ -227,31 +228,58 @@ __global__ void __launch_bounds__(SO_THREADS)
 
 // Sorts n pairs by the low `key_bits` bits of the key (stable).  keys[0]/vals[0] hold the input;
 // the two buffers ping-pong; returns the index (0/1) of the buffer that holds the result.
+// Scratch layout: [passes][256] digit histograms, 64 bytes of tile counters, [passes][tiles][256]
+// look-back status words.
+struct SortScratch {
+	uint32_t *ghist, *ctr;
+	unsigned long long *status;
+	uint64_t n_tiles;
+	int passes;
+};
+template <class K>
+static int sort_prepare(prt_b200 *c, DevBuf &scratch, uint64_t n, int key_bits, cudaStream_t s,
+                        SortScratch &sc) {
+	sc.passes = std::min<int>(sizeof(K), (key_bits + 7) / 8);
+	sc.n_tiles = (n + SO_TILE - 1) / SO_TILE;
+	const size_t hist_b = (size_t)SO_MAX_PASSES * SO_RADIX * 4, ctr_b = 64;
+	const size_t status_b = (size_t)sc.passes * sc.n_tiles * SO_RADIX * 8;
+	PRT_CUDA(c, scratch.reserve(hist_b + ctr_b + status_b));
+	char *base = scratch.as<char>();
+	sc.ghist = reinterpret_cast<uint32_t *>(base);
+	sc.ctr = reinterpret_cast<uint32_t *>(base + hist_b);
+	sc.status = reinterpret_cast<unsigned long long *>(base + hist_b + ctr_b);
+	PRT_CUDA(c, cudaMemsetAsync(base, 0, hist_b + ctr_b + status_b, s));
+	return PRT_OK;
+}
+
+// Sorts n pairs by the low `key_bits` bits of the key (stable).  keys[0]/vals[0] hold the input;
+// the two buffers ping-pong; returns the index (0/1) of the buffer that holds the result.
+// prepared != nullptr: the caller has called sort_prepare and accumulated the digit histograms
+// itself (the ray-key kernel does, saving one read of the keys).  identity_vals: vals[0] is not
+// read, the values are the positions 0..n-1.
 template <class K>
 static int radix_sort_pairs_t(prt_b200 *c, DevBuf &scratch, K *const keys[2], uint32_t *const vals[2],
-                              uint64_t n, int key_bits, cudaStream_t s, int *result_index) {
+                              uint64_t n, int key_bits, cudaStream_t s, int *result_index,
+                              const SortScratch *prepared = nullptr, bool identity_vals = false) {
 	*result_index = 0;
 	if (n <= 1 || key_bits <= 0)
 		return PRT_OK;
-	const int passes = std::min<int>(sizeof(K), (key_bits + 7) / 8);
-	const uint64_t n_tiles = (n + SO_TILE - 1) / SO_TILE;
-	const size_t hist_b = (size_t)SO_MAX_PASSES * SO_RADIX * 4, ctr_b = 64;
-	const size_t status_b = (size_t)passes * n_tiles * SO_RADIX * 8;
-	PRT_CUDA(c, scratch.reserve(hist_b + ctr_b + status_b));
-	char *base = scratch.as<char>();
-	uint32_t *ghist = reinterpret_cast<uint32_t *>(base);
-	uint32_t *ctr = reinterpret_cast<uint32_t *>(base + hist_b);
-	unsigned long long *status = reinterpret_cast<unsigned long long *>(base + hist_b + ctr_b);
-	PRT_CUDA(c, cudaMemsetAsync(base, 0, hist_b + ctr_b + status_b, s));
-	const int hgrid = (int)std::min<uint64_t>((n + SO_THREADS * 8 - 1) / (SO_THREADS * 8),
-	                                          (uint64_t)c->sm_count * 8);
-	k_sweep_hist<K><<<hgrid, SO_THREADS, 0, s>>>(keys[0], n, passes, ghist);
-	c->launches += 1;
+	SortScratch sc;
+	if (prepared) {
+		sc = *prepared;
+	} else {
+		if (int rc = sort_prepare<K>(c, scratch, n, key_bits, s, sc))
+			return rc;
+		const int hgrid = (int)std::min<uint64_t>((n + SO_THREADS * 8 - 1) / (SO_THREADS * 8),
+		                                          (uint64_t)c->sm_count * 8);
+		k_sweep_hist<K><<<hgrid, SO_THREADS, 0, s>>>(keys[0], n, sc.passes, sc.ghist);
+		c->launches += 1;
+	}
 	int cur = 0;
-	for (int p = 0; p < passes; ++p) {
-		k_sweep_pass<K><<<(unsigned)n_tiles, SO_THREADS, 0, s>>>(
-		    keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, 8 * p, ghist + p * SO_RADIX,
-		    status + (size_t)p * n_tiles * SO_RADIX, ctr + p);
+	for (int p = 0; p < sc.passes; ++p) {
+		k_sweep_pass<K><<<(unsigned)sc.n_tiles, SO_THREADS, 0, s>>>(
+		    keys[cur], (p == 0 && identity_vals) ? nullptr : vals[cur], keys[cur ^ 1], vals[cur ^ 1], n,
+		    8 * p, sc.ghist + p * SO_RADIX, sc.status + (size_t)p * sc.n_tiles * SO_RADIX, sc.ctr + p);
 		c->launches += 1;
 		cur ^= 1;
 	}
@@ -264,10 +292,30 @@ int radix_sort_pairs(prt_b200 *c, DevBuf &scratch, uint64_t *const keys[2], uint
                      uint64_t n, int key_bits, cudaStream_t s, int *result_index) {
 	return radix_sort_pairs_t<uint64_t>(c, scratch, keys, vals, n, key_bits, s, result_index);
 }
-// 32-bit keys (the ray reordering: <= 32 key bits): a pass moves 8 + 8 bytes per pair instead of 12 + 12
-int radix_sort_pairs32(prt_b200 *c, DevBuf &scratch, uint32_t *const keys[2], uint32_t *const vals[2],
-                       uint64_t n, int key_bits, cudaStream_t s, int *result_index) {
-	return radix_sort_pairs_t<uint32_t>(c, scratch, keys, vals, n, key_bits, s, result_index);
+// 32-bit keys (the ray reordering: <= 32 key bits; a pass moves 8 + 8 bytes per pair instead of
+// 12 + 12), in two steps for a caller that produces the keys on the device and can count their
+// digits while it does (trace.cu: k_ray_keys): prepare hands out the zeroed histogram
+// ([passes][256], digit p = bits 8p..8p+7), run sorts with values = positions.
+int radix_sort_prepare32(prt_b200 *c, DevBuf &scratch, uint64_t n, int key_bits, cudaStream_t s,
+                         uint32_t **ghist, int *passes) {
+	SortScratch sc;
+	if (int rc = sort_prepare<uint32_t>(c, scratch, n, key_bits, s, sc))
+		return rc;
+	*ghist = sc.ghist;
+	*passes = sc.passes;
+	return PRT_OK;
+}
+int radix_sort_run32_identity(prt_b200 *c, DevBuf &scratch, uint32_t *const keys[2], uint32_t *const vals[2],
+                              uint64_t n, int key_bits, cudaStream_t s, int *result_index) {
+	SortScratch sc; // same layout as prepare computed (scratch was reserved and zeroed there)
+	sc.passes = std::min<int>(sizeof(uint32_t), (key_bits + 7) / 8);
+	sc.n_tiles = (n + SO_TILE - 1) / SO_TILE;
+	const size_t hist_b = (size_t)SO_MAX_PASSES * SO_RADIX * 4, ctr_b = 64;
+	char *base = scratch.as<char>();
+	sc.ghist = reinterpret_cast<uint32_t *>(base);
+	sc.ctr = reinterpret_cast<uint32_t *>(base + hist_b);
+	sc.status = reinterpret_cast<unsigned long long *>(base + hist_b + ctr_b);
+	return radix_sort_pairs_t<uint32_t>(c, scratch, keys, vals, n, key_bits, s, result_index, &sc, true);
 }
 
 } // namespace prt

@@ -22,13 +22,18 @@ namespace prt {
 // ------------------------------------------------------------------------------------------------
 // Ray reordering.  Incoherent batches (bounce rays, random rays) make the 32 lanes of a warp walk
 // unrelated parts of the tree: every node fetch touches 32 different lines and lanes finish at
-// very different times.  Sorting the batch by a 24-bit key -- Morton code of the origin (4 bits per
-// axis inside the scene box) above the Morton code of the direction (4 bits per axis) -- puts rays
+// very different times.  Sorting the batch by a short key -- Morton code of the origin (3 bits per
+// axis inside the scene box) above the Morton code of the direction (2 bits per axis) -- puts rays
 // that start in the same region and point the same way next to each other.  The traversal then
 // processes rays in key order through a permutation; results are written to the rays' own slots,
 // so the output order is unchanged.  Measured x1.39 (10 M tris / random rays) and x1.45 (one-bounce
 // diffuse rays in the 262 k-tri interior); coherent primary rays gain nothing, which the key
 // kernel detects (most neighbouring rays already share their key) so that the sort is skipped.
+// Key width (sweep on the B200, traversal kernel ms / whole step ms): what the sort buys is mostly
+// lanes that agree on the order of the children; C4 (10^8 random rays) 27.35 / 31.03 with 4 + 4
+// bits (3 sort passes), 27.76 / 30.49 with 3 + 2 (2 passes), 27.64 / 29.43 with 1 + 1 (1 pass);
+// C3B (8.3 M bounce rays) 0.949 / 1.319, 1.028 / 1.312, 1.145 / 1.336.  3 + 2 is the default: never
+// worse than the 24-bit key on either, and it does not bet on uniformly random rays.
 __host__ __device__ __forceinline__ uint32_t spread4(uint32_t v) { // 4 bits -> every third bit
 	return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6);
 }
@@ -63,16 +68,31 @@ __device__ __forceinline__ uint32_t ray_key(const float *__restrict__ r, float3 
 
 // Sort key with `ob` bits per axis of the origin above `db` bits per axis of the direction (the
 // probe's fixed 4 + 4 key only decides WHETHER to sort).
+// Grid-stride over the batch; the digit histograms of the sort passes (digit p = key bits 8p..8p+7)
+// are counted on the way -- in shared memory, flushed once per block -- so that the sort does not
+// read the keys again for them; the values of the sort are the positions themselves and are not
+// written here (the first pass generates them).
 __global__ void __launch_bounds__(256)
     k_ray_keys(const float *__restrict__ rays, uint64_t n, float3 lo, float3 inv_ext, int ob, int db,
-               uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
-	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) {
-		const float *r = rays + i * 6;
-		const float ox = __ldg(r), oy = __ldg(r + 1), oz = __ldg(r + 2);
-		const float dx = __ldg(r + 3), dy = __ldg(r + 4), dz = __ldg(r + 5);
+               uint32_t *__restrict__ keys, int passes, uint32_t *__restrict__ ghist /* [passes][256] */) {
+	__shared__ uint32_t sh[4][256];
+	for (int p = 0; p < passes; ++p)
+		sh[p][threadIdx.x] = 0;
+	__syncthreads();
+	const float no = (float)(1 << ob), nd = (float)(1 << db);
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const float2 *r = reinterpret_cast<const float2 *>(rays + i * 6); // (6 floats: 8-byte aligned
+		float ox, oy, oz, dx, dy, dz;                                     // whenever the batch is)
+		if ((reinterpret_cast<uintptr_t>(rays) & 7) == 0) {
+			const float2 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
+			ox = a.x, oy = a.y, oz = b.x, dx = b.y, dy = c.x, dz = c.y;
+		} else {
+			const float *f = rays + i * 6;
+			ox = __ldg(f), oy = __ldg(f + 1), oz = __ldg(f + 2), dx = __ldg(f + 3), dy = __ldg(f + 4),
+			dz = __ldg(f + 5);
+		}
 		const float inv = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-37f));
-		const float no = (float)(1 << ob), nd = (float)(1 << db);
 		// NaN / out-of-box values clamp into the grid; the key only steers the processing order
 		const uint32_t qx = (uint32_t)fminf(fmaxf((ox - lo.x) * inv_ext.x * no, 0.f), no - 1.f);
 		const uint32_t qy = (uint32_t)fminf(fmaxf((oy - lo.y) * inv_ext.y * no, 0.f), no - 1.f);
@@ -80,8 +100,28 @@ __global__ void __launch_bounds__(256)
 		const uint32_t ux = (uint32_t)fminf(fmaxf((dx * inv * 0.5f + 0.5f) * nd, 0.f), nd - 1.f);
 		const uint32_t uy = (uint32_t)fminf(fmaxf((dy * inv * 0.5f + 0.5f) * nd, 0.f), nd - 1.f);
 		const uint32_t uz = (uint32_t)fminf(fmaxf((dz * inv * 0.5f + 0.5f) * nd, 0.f), nd - 1.f);
-		keys[i] = (uint32_t)((morton3(qx, qy, qz) << (3 * db)) | morton3(ux, uy, uz)); // 3 (ob + db) <= 32 bits
-		vals[i] = (uint32_t)i;
+		const uint32_t key = (uint32_t)((morton3(qx, qy, qz) << (3 * db)) | morton3(ux, uy, uz)); // 3 (ob + db) <= 32 bits
+		keys[i] = key;
+		const unsigned act = __activemask();
+		for (int p = 0; p < passes; ++p) {
+			// a digit that is constant across the warp (unused high bits, neighbouring rays of a
+			// half-sorted batch) would serialise 32 same-address atomics: aggregate it into one
+			const uint32_t d = (key >> (8 * p)) & 0xff;
+			int same;
+			__match_all_sync(act, d, &same);
+			if (same) {
+				if ((threadIdx.x & 31) == (__ffs(act) - 1))
+					atomicAdd(&sh[p][d], (uint32_t)__popc(act));
+			} else {
+				atomicAdd(&sh[p][d], 1u);
+			}
+		}
+	}
+	__syncthreads();
+	for (int p = 0; p < passes; ++p) {
+		const uint32_t c = sh[p][threadIdx.x];
+		if (c)
+			atomicAdd(&ghist[p * 256 + threadIdx.x], c);
 	}
 }
 
@@ -301,14 +341,19 @@ int launch_trace(prt_b200 *c, const float *d_rays6, uint64_t n, uint32_t mask, c
 			do_sort = same * 2 < pairs;
 		}
 		if (do_sort) {
-			k_ray_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
-			    d_rays6, n, lo, ie, c->ray_key_ob, c->ray_key_db, rs.keys[0].as<uint32_t>(),
-			    rs.vals[0].as<uint32_t>());
+			const int key_bits = 3 * (c->ray_key_ob + c->ray_key_db);
+			uint32_t *ghist = nullptr;
+			int passes = 0;
+			if (int rc = radix_sort_prepare32(c, rs.scratch, n, key_bits, s, &ghist, &passes))
+				return rc;
+			const unsigned kgrid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)c->sm_count * 16);
+			k_ray_keys<<<kgrid, 256, 0, s>>>(d_rays6, n, lo, ie, c->ray_key_ob, c->ray_key_db,
+			                                 rs.keys[0].as<uint32_t>(), passes, ghist);
 			c->launches += 1;
 			uint32_t *const kk[2] = {rs.keys[0].as<uint32_t>(), rs.keys[1].as<uint32_t>()};
 			uint32_t *const vv[2] = {rs.vals[0].as<uint32_t>(), rs.vals[1].as<uint32_t>()};
 			int cur = 0;
-			if (int rc = radix_sort_pairs32(c, rs.scratch, kk, vv, n, 3 * (c->ray_key_ob + c->ray_key_db), s, &cur))
+			if (int rc = radix_sort_run32_identity(c, rs.scratch, kk, vv, n, key_bits, s, &cur))
 				return rc;
 			P.perm = vv[cur];
 			c->sorted_batches++;
