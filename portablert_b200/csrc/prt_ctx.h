@@ -139,7 +139,7 @@ struct prt_b200 {
 	prt::DevBuf coop_buf[2], coop_lifo[2]; // cooperative tail (prt_trace_kernel.cuh: k_coop): handed-over rays, LIFOs
 	const void *coop_seen[2] = {nullptr, nullptr};
 	int coop_min_sp = 0;      // env PRT_B200_COOP_SP: ... for rays with at least this many stacked subtrees
-	int coop_blocks = 4;      // env PRT_B200_COOP_BLOCKS: blocks per SM of the follow-up kernel
+	int coop_blocks = 8;      // env PRT_B200_COOP_BLOCKS: blocks per SM of the follow-up kernel
 	int coop_after = 4;       // env PRT_B200_COOP: iterations past the end of the batch before a warp goes cooperative (0 = never)
 	// the exact pass of the last EXOTIC_DEFERRED launch (trace.cu: finish_exotic)
 	bool pending_exotic = false;

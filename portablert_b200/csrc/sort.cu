@@ -222,7 +222,8 @@ __global__ void __launch_bounds__(SO_THREADS, (sizeof(K) == 4 ? 4 : 3))
 			const K kk = s_keys[i];
 			const uint32_t d = (uint32_t)((kk >> shift) & 0xff);
 			const long long g = gofs[d] + i;
-			keys_out[g] = kk;
+			if (keys_out) // (nullptr: the last pass of a sort whose caller only wants the values)
+				keys_out[g] = kk;
 			vals_out[g] = s_vals[i];
 		}
 	}
@@ -262,7 +263,8 @@ static int sort_prepare(prt_b200 *c, DevBuf &scratch, uint64_t n, int key_bits, 
 template <class K>
 static int radix_sort_pairs_t(prt_b200 *c, DevBuf &scratch, K *const keys[2], uint32_t *const vals[2],
                               uint64_t n, int key_bits, cudaStream_t s, int *result_index,
-                              const SortScratch *prepared = nullptr, bool identity_vals = false) {
+                              const SortScratch *prepared = nullptr, bool identity_vals = false,
+                              bool keep_keys = true) {
 	*result_index = 0;
 	if (n <= 1 || key_bits <= 0)
 		return PRT_OK;
@@ -280,7 +282,8 @@ static int radix_sort_pairs_t(prt_b200 *c, DevBuf &scratch, K *const keys[2], ui
 	int cur = 0;
 	for (int p = 0; p < sc.passes; ++p) {
 		k_sweep_pass<K><<<(unsigned)sc.n_tiles, SO_THREADS, 0, s>>>(
-		    keys[cur], (p == 0 && identity_vals) ? nullptr : vals[cur], keys[cur ^ 1], vals[cur ^ 1], n,
+		    keys[cur], (p == 0 && identity_vals) ? nullptr : vals[cur],
+		    (p == sc.passes - 1 && !keep_keys) ? nullptr : keys[cur ^ 1], vals[cur ^ 1], n,
 		    8 * p, sc.ghist + p * SO_RADIX, sc.status + (size_t)p * sc.n_tiles * SO_RADIX, sc.ctr + p);
 		c->launches += 1;
 		cur ^= 1;
@@ -317,7 +320,8 @@ int radix_sort_run32_identity(prt_b200 *c, DevBuf &scratch, uint32_t *const keys
 	sc.ghist = reinterpret_cast<uint32_t *>(base);
 	sc.ctr = reinterpret_cast<uint32_t *>(base + hist_b);
 	sc.status = reinterpret_cast<unsigned long long *>(base + hist_b + ctr_b);
-	return radix_sort_pairs_t<uint32_t>(c, scratch, keys, vals, n, key_bits, s, result_index, &sc, true);
+	return radix_sort_pairs_t<uint32_t>(c, scratch, keys, vals, n, key_bits, s, result_index, &sc, true,
+	                                    false); // (the traversal reads the permutation only)
 }
 
 } // namespace prt
