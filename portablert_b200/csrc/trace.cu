@@ -238,7 +238,9 @@ static int launch_kernel(prt_b200 *c, KernelFn fn, int cache_slot, uint32_t mask
 	P.coop_after = 0;
 	const bool use_coop = coop && c->coop_after > 0;
 	constexpr uint32_t COOP_CAP = 8192;
-	const int coop_grid = c->sm_count * c->coop_blocks;
+	// (8 blocks per SM measured best on a 2 M-ray batch, 4 on the 260 k-ray chunks of the host pipeline,
+	// where an almost empty follow-up kernel is pure launch and drain time)
+	const int coop_grid = c->sm_count * (n >= (1ull << 20) ? c->coop_blocks : std::min(c->coop_blocks, 4));
 	if (use_coop) {
 		const uint32_t depth = (uint32_t)stack_bound(c, false) + 1;
 		const uint32_t rec = COOP_PARK + 2 * depth;
