@@ -806,7 +806,7 @@ def main():
     # algorithmic HBM bytes per triangle: bounds 36 R; morton 36 R + 12 W; histograms
     # 8 R; P sort passes x (12 R + 12 W); hierarchy kernel: 4 (index) + 36 (triangle) + 16 (keys) R,
     # 64 W (record), 64 W (node halves), 24 R (sibling box), 8 (bound exchange)
-    passes = 4 if n_tris <= (1 << 16) else (5 if n_tris <= (1 << 22) else 6)
+    passes = 4 if n_tris <= (1 << 16) else (5 if n_tris <= (1 << 24) else 6)  # build.cu: morton_bits_for
     build_bytes_per_tri = 36 + 48 + 8 + 24 * passes + 56 + 64 + 64 + 24 + 8
     build = {"mtris_s": n_tris / (build_ms_mean * 1e-3) / 1e6, "ms": build_ms_mean,
              "ms_with_optimisation": float(np.mean(build_opt_ms)),
