@@ -195,10 +195,13 @@ def test_wide_quantised_nodes_are_conservative_and_change_nothing(emu, oracle):
     assert np.array_equal(a["t"], b["t"]) and np.array_equal(a["pid"], b["pid"])
 
 
-def test_wide_node_boxes_contain_their_children(emu):
+@pytest.mark.parametrize("scale", [1.0, 2.0 ** -100, 3.0e-38, 2.0 ** 100, 1.0e37])
+def test_wide_node_boxes_contain_their_children(emu, scale):
     """Dequantised child boxes of every wide node contain the exact child boxes (up to the
-    half-ulp saturation case the traversal margin covers)."""
-    tris = scenes.interior(5000)
+    half-ulp saturation case the traversal margin covers) -- also for scenes whose quantisation
+    scales sit at the ends of the exponent range (the quantiser multiplies by the exact reciprocal
+    of its power-of-two scale, a subnormal for the largest scenes)."""
+    tris = (scenes.interior(5000).astype(np.float64) * scale).astype(np.float32)
     emu.build(tris, 13)
     nodes, _ = emu.download()
     wide = emu.download_wide()
