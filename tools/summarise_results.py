@@ -116,8 +116,9 @@ def main():
                    "e2e ms/step | copy floor ms | e2e digest == ranks' device results | replicas identical |")
         out.append("|---:|---:|---:|---:|---:|---:|---:|---|---|")
         out += rows
-        out.append("\n(The N >= 2 rows were measured one commit before the 15-bit ray key and the fused key "
-                   "histogram; N = 1 then read 3221 Mrays/s device-timed.)")
+        out.append("\n(The N = 4 and N = 8 rows were measured one commit before the 15-bit ray key and the fused "
+                   "key histogram, when N = 1 / 2 read 3221 / 6390 Mrays/s device-timed; every row on a different box, "
+                   "whose host<->device paths differ: see the floor column.)")
         out.append("\nThe device-timed metric scales with the GPUs (no collective on the data path).  The e2e "
                    "call is bound by the box's shared host<->device path (about 130 GB/s in total on these "
                    "virtual machines): it runs at the copy floor from N = 2 on.\n")
