@@ -81,3 +81,48 @@ def test_acceptance_program_on_the_cuda_backend(tmp_path):
     assert len(cuda) == 14 and all(r[-1] == "1" for r in cuda), cuda
     assert "Testing CUDA" in out.stdout and "B200" in out.stdout
     print(out.stdout)
+
+
+REF = "/root/reference"
+
+
+def test_use_cuda_block_configures_and_builds_in_the_reference_cmake(tmp_path):
+    """The USE_CUDA block (cmake/portableRT_use_cuda.cmake) inside the reference's OWN
+    CMakeLists.txt: a staged copy of the checkout (patched by tools/patch_reference.py; staged under
+    tmp, never committed) with the block included where the other backend blocks sit, configured
+    with -DUSE_CUDA=ON and built.  The examples sub-directory is left out: it needs SDL2 and four
+    network fetches.  CPU only: nothing runs, the plugin just has to compile and link in."""
+    import shutil
+    import sys
+    lib = os.path.join(ROOT, "portablert_b200", "libprt_b200.so")
+    cmake = shutil.which("cmake")
+    if not os.path.isdir(REF) or cmake is None or not os.path.exists(lib):
+        pytest.skip("needs /root/reference, cmake and the built library")
+    stage = tmp_path / "portableRT"
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "patch_reference.py"), REF, str(stage)],
+                   check=True, capture_output=True)
+    shutil.copy(os.path.join(REF, "src", "portableRT.cpp"), stage / "src")
+    shutil.copy(os.path.join(REF, "version.hpp.in"), stage)
+    text = open(os.path.join(REF, "CMakeLists.txt")).read()
+    assert "add_subdirectory(examples)" in text
+    text = text.replace("add_subdirectory(examples)", "")
+    marker = "set_target_properties(portableRT PROPERTIES \n    RUNTIME_OUTPUT_DIRECTORY"
+    assert marker in text, "the reference's CMakeLists.txt changed shape"
+    block = os.path.join(ROOT, "cmake", "portableRT_use_cuda.cmake")
+    text = text.replace(marker, f"include({block})\n\n" + marker)
+    (stage / "CMakeLists.txt").write_text(text)
+    build = tmp_path / "build"
+    cfg = subprocess.run([cmake, "-S", str(stage), "-B", str(build), "-DUSE_CUDA=ON",
+                          f"-DPRT_B200_ROOT={ROOT}", "-DCMAKE_BUILD_TYPE=Release",
+                          "-DCMAKE_CXX_FLAGS=-include cstdint"],
+                         capture_output=True, text=True, timeout=300)
+    assert cfg.returncode == 0, cfg.stdout + cfg.stderr
+    cache = (build / "CMakeCache.txt").read_text()
+    assert "libprt_b200.so" in cache and "USE_CUDA:BOOL=ON" in cache
+    bld = subprocess.run([cmake, "--build", str(build), "-j", "4"], capture_output=True, text=True,
+                         timeout=600)
+    assert bld.returncode == 0, bld.stdout[-3000:] + bld.stderr[-3000:]
+    archive = build / "lib" / "libportableRT.a"
+    assert archive.exists()
+    syms = subprocess.run(["nm", "-C", str(archive)], capture_output=True, text=True).stdout
+    assert "CUDABackend" in syms and "prt_b200_create" in syms  # the plugin is in, the C ABI referenced
